@@ -1,0 +1,136 @@
+/* sdfk.h -- C ABI of libsdfk.so: the B200-native replacement for SdfKit's data-parallel hot path.
+ *
+ * The reference (praeclarum/SdfKit, pure C#) has no FFI; the seam it offers is managed: the `Sdf`
+ * delegate produced by SdfExprEx.ToSdf and consumed by Voxels.SampleSdf / SdfEx.ToVoxels / ToMesh /
+ * ToImage / RayMarcher, plus the data-only entry MarchingCubes.CreateMesh(Voxels,...).  These are the
+ * entry points a P/Invoke shim binds to put the GPU behind that seam (INTEGRATION.md shows the C# side).
+ * Each function cites the reference interface it replaces (paths relative to the SdfKit repository).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on failure; sdfk_last_error() returns the message of the
+ *     last failure on the calling thread.  No C++ exception crosses this boundary.
+ *   - the caller owns every host buffer it passes; the library never keeps a host pointer after return.
+ *   - handles are released only by their *_destroy function.
+ *   - all entry points taking a ctx are serialised per ctx (internal mutex); one ctx drives one GPU
+ *     (one process per GPU; a multi-GPU job shards by z-slab / row band).
+ *   - matrices are 16 floats, row-major System.Numerics.Matrix4x4 (M11 M12 M13 M14 M21 ...), row-vector
+ *     convention; the caller computes them (the C# shim with System.Numerics itself).
+ *   - device layout of voxels is x-fastest; the C# `[x,y,z]` layout appears only in import/export.
+ */
+#ifndef SDFK_H
+#define SDFK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFK_OK 0
+#define SDFK_ERR_INVALID (-1)      /* bad argument */
+#define SDFK_ERR_CUDA (-2)         /* CUDA runtime / driver failure */
+#define SDFK_ERR_COMPILE (-3)      /* NVRTC rejected the SDF source (the log is in sdfk_last_error) */
+#define SDFK_ERR_UNSUPPORTED (-4)  /* e.g. an opaque (non-SdfExpr) SDF, grid too large for 32-bit cell ids */
+#define SDFK_ERR_INTERNAL (-5)
+
+typedef struct sdfk_ctx sdfk_ctx;
+typedef struct sdfk_sdf sdfk_sdf;
+typedef struct sdfk_voxels sdfk_voxels;
+typedef struct sdfk_mesh sdfk_mesh;
+
+/* IProgress<float>.Report (MarchingCubes.cs:81): called on the calling thread with z/nz_bound per layer. */
+typedef void (*sdfk_progress_fn)(float fraction, void* user);
+
+const char* sdfk_last_error(void);
+int sdfk_version(void);
+
+/* ---- context: one GPU, one stream --------------------------------------------------------------- */
+int sdfk_ctx_create(int device, sdfk_ctx** out);
+/* same, launching on a caller-owned cudaStream_t (e.g. the host framework's current stream) */
+int sdfk_ctx_create_on_stream(int device, void* cuda_stream, sdfk_ctx** out);
+int sdfk_ctx_destroy(sdfk_ctx* ctx);
+int sdfk_ctx_synchronize(sdfk_ctx* ctx);
+int sdfk_ctx_stream(sdfk_ctx* ctx, void** cuda_stream);
+/* CUDA-event stopwatch on the ctx stream (device time between the two calls) */
+int sdfk_ctx_timer_start(sdfk_ctx* ctx);
+int sdfk_ctx_timer_stop(sdfk_ctx* ctx, float* milliseconds);
+/* how many kernels this ctx has launched so far */
+int sdfk_ctx_launch_count(sdfk_ctx* ctx, int64_t* launches);
+
+/* ---- SdfExpr.ToSdf(): SdfExprCompiler.Compile (SdfExpr.cs:208-211,234-271) ------------------------
+ * body = statements of `sk_float4 sdf_eval(sk_float3 p)` in the SDF source dialect (csrc/sdfk_prelude.h),
+ * produced by lowering the expression tree.  NVRTC-compiled for sm_100a without FMA contraction.       */
+int sdfk_sdf_compile(sdfk_ctx* ctx, const char* body, size_t len, sdfk_sdf** out);
+int sdfk_sdf_destroy(sdfk_sdf* sdf);
+/* NVRTC-compile only (needs no GPU): validates a body and reports the cubin size. */
+int sdfk_sdf_check(const char* body, size_t len, size_t* cubin_bytes);
+/* the Sdf delegate itself (Sdf.cs:8): rgbd[i] = sdf(xyz[i]); host pointers, n*3 floats in, n*4 out */
+int sdfk_sdf_eval(sdfk_sdf* sdf, const float* xyz, float* rgbd, int64_t n);
+
+/* ---- Voxels (Voxels.cs) ---------------------------------------------------------------------------
+ * SdfEx.ToVoxels / Voxels.SampleSdf (+ ClipToBounds when clip != 0) (Sdf.cs:49-57, Voxels.cs:72-167).
+ * Asynchronous on the ctx stream; the voxels stay resident in HBM.                                     */
+int sdfk_voxels_sample(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const float max[3],
+                       int nx, int ny, int nz, int clip, sdfk_voxels** out);
+/* one z-slab [z_begin, z_end) of the same nx*ny*nz grid (multi-GPU sharding; halo slices are resampled) */
+int sdfk_voxels_sample_slab(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const float max[3],
+                            int nx, int ny, int nz, int clip, int z_begin, int z_end, sdfk_voxels** out);
+/* re-sample into an existing voxels object (same grid; no allocation) -- the steady-state hot call */
+int sdfk_voxels_resample(sdfk_voxels* vox, sdfk_sdf* sdf, int clip);
+/* new Voxels(values, colors, min, max) (Voxels.cs:23-35): host arrays in C# layout
+ * values[nx][ny][nz], colors[nx][ny][nz][3] (colors may be NULL = zeros)                                */
+int sdfk_voxels_import(sdfk_ctx* ctx, const float* values, const float* colors, const float min[3],
+                       const float max[3], int nx, int ny, int nz, sdfk_voxels** out);
+/* Voxels.Values / Voxels.Colors (Voxels.cs:8-9) in C# layout; either pointer may be NULL.  For a slab the
+ * arrays are [nx][ny][z_end - z_begin].                                                                 */
+int sdfk_voxels_export(sdfk_voxels* vox, float* values, float* colors);
+/* Voxels.ClipToBounds (Voxels.cs:133-167) on resident voxels */
+int sdfk_voxels_clip(sdfk_voxels* vox);
+/* dims = {nx, ny, nz, z_begin, z_end}; device pointers to the x-fastest arrays (dist, rgb) */
+int sdfk_voxels_info(sdfk_voxels* vox, int dims[5], void** dist_dev, void** rgb_dev);
+int sdfk_voxels_destroy(sdfk_voxels* vox);
+
+/* ---- MarchingCubes.CreateMesh / Voxels.ToMesh (MarchingCubes.cs:39-92, Voxels.cs:67-70) -------------
+ * transform / normal_transform: the matrices Mesh.Transform applies (MarchingCubes.cs:85-90, Mesh.cs:47-64),
+ * computed by the caller; both NULL leaves the mesh in voxel-index space.                               */
+int sdfk_mesh_create(sdfk_ctx* ctx, sdfk_voxels* vox, float iso, int step, const float transform[16],
+                     const float normal_transform[16], sdfk_progress_fn progress, void* user, sdfk_mesh** out);
+/* Slab meshing for multi-GPU jobs, in two phases around the caller's all-gather of counts:
+ *   sdfk_mesh_classify: classify + scan the cell layers of this slab that lie in [k_begin, k_end) (global
+ *                       cell-layer range this rank owns); reports how many vertices / triangles it owns.
+ *   sdfk_mesh_emit:     write the owned vertices / triangles with global ids starting at vertex_base /
+ *                       triangle_base (exclusive sums of the lower ranks' counts).                      */
+int sdfk_mesh_classify(sdfk_ctx* ctx, sdfk_voxels* vox, float iso, int step, int k_begin, int k_end,
+                       sdfk_mesh** out, int64_t* nverts, int64_t* ntris);
+int sdfk_mesh_emit(sdfk_mesh* mesh, int64_t vertex_base, int64_t triangle_base, const float transform[16],
+                   const float normal_transform[16]);
+int sdfk_mesh_counts(sdfk_mesh* mesh, int64_t* nverts, int64_t* ntris);
+/* Mesh.Vertices/Colors/Normals/Triangles + Min/Max (Mesh.cs:10-18): any pointer may be NULL.
+ * aabb = {min.x, min.y, min.z, max.x, max.y, max.z}                                                     */
+int sdfk_mesh_export(sdfk_mesh* mesh, float* vertices, float* colors, float* normals, int32_t* triangles,
+                     float aabb[6]);
+int sdfk_mesh_device_ptrs(sdfk_mesh* mesh, void** vertices, void** colors, void** normals, void** triangles);
+/* stats[0..3] = device ms of classify, scan, compact, emit; stats[4] = active cells */
+int sdfk_mesh_stats(sdfk_mesh* mesh, double stats[8]);
+int sdfk_mesh_destroy(sdfk_mesh* mesh);
+
+/* ---- RayMarcher (RayMarcher.cs) ---------------------------------------------------------------------
+ * cam_pos = translation of inverse(ViewTransform); inv_view_proj = inverse(ViewTransform * projection)
+ * (RayMarcher.cs:95-108) -- computed by the caller.  rows [row_begin, row_end) of the w*h image are
+ * rendered into rgb (host, (row_end-row_begin)*w*3 floats) -- the reference's row bands (RayMarcher.cs:50-61). */
+int sdfk_render(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3], const float inv_view_proj[16],
+                float near_plane, float far_plane, int iterations, int row_begin, int row_end, float* rgb);
+/* RayMarcher.RenderDepth (RayMarcher.cs:69-93): depth host buffer of (row_end-row_begin)*w floats */
+int sdfk_render_depth(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3],
+                      const float inv_view_proj[16], float near_plane, int iterations, int row_begin, int row_end,
+                      float* depth);
+/* same kernels writing to device memory, asynchronous on the ctx stream */
+int sdfk_render_device(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3],
+                       const float inv_view_proj[16], float near_plane, float far_plane, int iterations,
+                       int row_begin, int row_end, void* rgb_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFK_H */

@@ -138,3 +138,21 @@ def readme_color(i, p, d):
 def readme_scene():
     """SdfExprs.Sphere(0.5f).RepeatXY(1.125f, 1.125f, colour lambda) -- BASELINE configs 2/4/5."""
     return repeat(sphere(0.5), sx=f32(2.25) * f32(0.5), sy=f32(2.25) * f32(0.5), color_mod=readme_color)
+
+
+def perf_scene():
+    """Perf/Program.cs:5-22: Union(RepeatXY spheres, RepeatXZ boxes)."""
+    s = f32(2.25) * f32(0.5)
+    boxes = repeat(box(f32(0.5) / f32(2)), sx=s, sz=s, color_mod=readme_color)
+    spheres = repeat(sphere(0.5), sx=s, sy=s, color_mod=readme_color)
+    return union(spheres, boxes)
+
+
+def csg50(parts):
+    """BASELINE config 3 from the part list of sdfkit_b200.scenes.csg50_parts() (data only)."""
+    tree = None
+    for kind, args, c, col in parts:
+        prim = [sphere, box, cylinder][kind](*args)
+        prim = with_color(translate(prim, c), col)
+        tree = prim if tree is None else union(tree, prim)
+    return repeat(subtract(tree, sphere(0.5)), sx=2.5, sy=2.5)

@@ -1,0 +1,148 @@
+"""ctypes binding of libsdfk.so (include/sdfk.h).  The product path: fails loudly when the CUDA
+library is missing or a call fails -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdfk.so")
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_float, C.c_void_p)
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes).  Every symbol include/sdfk.h declares is listed here.
+SIGNATURES = {
+    "sdfk_last_error": (C.c_char_p, []),
+    "sdfk_version": (C.c_int, []),
+    "sdfk_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "sdfk_ctx_create_on_stream": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "sdfk_ctx_destroy": (C.c_int, [_vp]),
+    "sdfk_ctx_synchronize": (C.c_int, [_vp]),
+    "sdfk_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "sdfk_ctx_timer_start": (C.c_int, [_vp]),
+    "sdfk_ctx_timer_stop": (C.c_int, [_vp, _fp]),
+    "sdfk_ctx_launch_count": (C.c_int, [_vp, _i64p]),
+    "sdfk_sdf_compile": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
+    "sdfk_sdf_destroy": (C.c_int, [_vp]),
+    "sdfk_sdf_check": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdfk_sdf_eval": (C.c_int, [_vp, _fp, _fp, C.c_int64]),
+    "sdfk_voxels_sample": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "sdfk_voxels_sample_slab": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(_vp)]),
+    "sdfk_voxels_resample": (C.c_int, [_vp, _vp, C.c_int]),
+    "sdfk_voxels_import": (C.c_int, [_vp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "sdfk_voxels_export": (C.c_int, [_vp, _fp, _fp]),
+    "sdfk_voxels_clip": (C.c_int, [_vp]),
+    "sdfk_voxels_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sdfk_voxels_destroy": (C.c_int, [_vp]),
+    "sdfk_mesh_create": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _fp, _fp, PROGRESS_FN, _vp, C.POINTER(_vp)]),
+    "sdfk_mesh_classify": (C.c_int, [_vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _i64p, _i64p]),
+    "sdfk_mesh_emit": (C.c_int, [_vp, C.c_int64, C.c_int64, _fp, _fp]),
+    "sdfk_mesh_counts": (C.c_int, [_vp, _i64p, _i64p]),
+    "sdfk_mesh_export": (C.c_int, [_vp, _fp, _fp, _fp, C.POINTER(C.c_int32), _fp]),
+    "sdfk_mesh_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sdfk_mesh_stats": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "sdfk_mesh_destroy": (C.c_int, [_vp]),
+    "sdfk_render": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
+    "sdfk_render_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
+    "sdfk_render_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, _vp]),
+}
+
+
+class SdfkError(RuntimeError):
+    """A libsdfk call failed (status < 0); the message is sdfk_last_error()."""
+
+    def __init__(self, code, message):
+        super().__init__("libsdfk error %d: %s" % (code, message))
+        self.code = code
+
+
+class NotSupportedError(NotImplementedError):
+    """The reference would run this on the CPU (e.g. an opaque lambda Sdf); the GPU path rejects it."""
+
+
+_lib = None
+
+
+def lib():
+    """Load libsdfk.so (built in-tree by sdfkit_b200/build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libsdfk.so is missing (%s): build it with `python -m sdfkit_b200.build` -- the SdfKit GPU path "
+                "has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)     # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise SdfkError(code, (lib().sdfk_last_error() or b"").decode("utf-8", "replace"))
+
+
+def fptr(a):
+    return None if a is None else a.ctypes.data_as(_fp)
+
+
+def f32c(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class Context:
+    """sdfk_ctx: one GPU + one stream.  `default()` gives the per-process context (LOCAL_RANK aware)."""
+    _default = None
+
+    def __init__(self, device=None, stream=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = _vp()
+        if stream is None:
+            check(lib().sdfk_ctx_create(int(device), C.byref(h)))
+        else:
+            check(lib().sdfk_ctx_create_on_stream(int(device), _vp(int(stream)), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    @classmethod
+    def default(cls):
+        if cls._default is None:
+            cls._default = cls()
+        return cls._default
+
+    def synchronize(self):
+        check(lib().sdfk_ctx_synchronize(self.handle))
+
+    def stream(self):
+        s = _vp()
+        check(lib().sdfk_ctx_stream(self.handle, C.byref(s)))
+        return s.value or 0
+
+    def timer_start(self):
+        check(lib().sdfk_ctx_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().sdfk_ctx_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        check(lib().sdfk_ctx_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.handle:
+            lib().sdfk_ctx_destroy(self.handle)
+            self.handle = None
+            if Context._default is self:
+                Context._default = None

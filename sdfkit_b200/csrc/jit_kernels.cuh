@@ -1,0 +1,203 @@
+// jit_kernels.cuh -- kernels instantiated per SdfExpr by NVRTC (sm_100a).
+//
+// This text is appended, at sdfk_sdf_compile() time, after csrc/sdfk_prelude.h and the lowered
+//     SK_FN sk_float4 sdf_eval(sk_float3 p) { <body> }
+// and compiled with --fmad=false --prec-div=true --prec-sqrt=true --ftz=false so that every float
+// operation is the IEEE binary32 operation the reference's CPU path performs.
+// It must not include any header (NVRTC gets no include path).
+//
+//   sdfk_k_sample        K1  Voxels.SampleSdf + ClipToBounds      SdfKit/Voxels.cs:72-125,133-167
+//   sdfk_k_eval          K6  the Sdf delegate on a point batch    SdfKit/SdfExpr.cs:240-271
+//   sdfk_k_render        K5  RayMarcher.Render                    SdfKit/RayMarcher.cs:95-204
+//   sdfk_k_render_depth      RayMarcher.RenderDepth               SdfKit/RayMarcher.cs:69-93
+
+struct sdfk_fastdiv { unsigned mul, sh1, sh2; };   // q = n / d for 32-bit n (host-computed magic)
+
+static __device__ __forceinline__ unsigned sdfk_div(unsigned n, sdfk_fastdiv d)
+{
+    unsigned t = __umulhi(d.mul, n);
+    return (t + ((n - t) >> d.sh1)) >> d.sh2;
+}
+
+struct sdfk_sample_params {
+    float m0, m1, m2;          // min + 0.5*delta                               (Voxels.cs:81)
+    float dx, dy, dz;          // delta = (max-min)/n                           (Voxels.cs:32-34)
+    float clip_value;          // Size.X / NX                                   (Voxels.cs:139)
+    int clip;                  // ClipToBounds fused as a predicate
+    int nx, ny, nz;            // dimensions of the WHOLE grid
+    int z_begin;               // first z slice held by this slab
+    unsigned rows;             // ny * (slices in this slab)
+    unsigned tiles_per_row;    // ceil(nx / 128)
+    unsigned ntiles;           // rows * tiles_per_row
+    sdfk_fastdiv div_tpr, div_ny;
+};
+
+#define SDFK_SAMPLE_WARPS 8
+
+// Device layout (DESIGN.md "data layout"): x fastest.  dist[(zl*ny + y)*nx + x], rgb[((zl*ny + y)*nx + x)*3 + c],
+// zl = z - z_begin.  One warp handles a tile of 128 consecutive x of one row: every lane evaluates 4
+// consecutive voxels, the 4 distances leave as one float4 (512 B per warp store) and the 12 colour floats
+// are transposed through a warp-private shared-memory stage so that the 1536 B of colours also leave as
+// three fully coalesced 512 B float4 stores.  Streaming (evict-first) stores: the field is write-once.
+extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
+sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __restrict__ rgb)
+{
+    __shared__ float4 stage[SDFK_SAMPLE_WARPS][96];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    float4* const st = stage[warp];
+    const bool vec = (P.nx & 3) == 0;
+
+    for (unsigned tile = blockIdx.x * SDFK_SAMPLE_WARPS + warp; tile < P.ntiles; tile += gridDim.x * SDFK_SAMPLE_WARPS) {
+        const unsigned row = sdfk_div(tile, P.div_tpr);
+        const unsigned xc = tile - row * P.tiles_per_row;
+        const unsigned zl = sdfk_div(row, P.div_ny);
+        const int iy = (int)(row - zl * (unsigned)P.ny);
+        const int iz = (int)zl + P.z_begin;
+        const int x0 = (int)(xc * 128u + lane * 4u);
+
+        const float py = P.m1 + (float)iy * P.dy;     // p = min' + i*delta, one mul + one add (Voxels.cs:104-106)
+        const float pz = P.m2 + (float)iz * P.dz;
+        const bool yz_wall = P.clip && (iy == 0 || iy == P.ny - 1 || iz == 0 || iz == P.nz - 1);
+        const float fx0 = (float)x0;                  // exact; fx0 + k is exact below 2^24
+
+        float d[4];
+        float c[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float px = P.m0 + (fx0 + (float)k) * P.dx;
+            const sk_float4 r = sdf_eval(sk_make3(px, py, pz));
+            const int ix = x0 + k;
+            const bool wall = yz_wall || (P.clip && (ix == 0 || ix == P.nx - 1));
+            d[k] = wall ? P.clip_value : r.w;
+            c[3 * k + 0] = r.x;
+            c[3 * k + 1] = r.y;
+            c[3 * k + 2] = r.z;
+        }
+
+        const size_t vbase = (size_t)row * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
+        if (vec) {
+            const int nvalid = min(128, P.nx - (int)(xc * 128u));                // multiple of 4
+            if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
+            st[lane * 3 + 0] = make_float4(c[0], c[1], c[2], c[3]);
+            st[lane * 3 + 1] = make_float4(c[4], c[5], c[6], c[7]);
+            st[lane * 3 + 2] = make_float4(c[8], c[9], c[10], c[11]);
+            __syncwarp();
+            float4* const g = reinterpret_cast<float4*>(rgb + vbase * 3);
+            const int nq = (nvalid * 3) >> 2;                                    // float4s of colour in this tile
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int q = (int)lane + 32 * k;
+                if (q < nq) __stcs(g + q, st[q]);
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (x0 + k < P.nx) {
+                    const size_t v = vbase + lane * 4u + k;
+                    dist[v] = d[k];
+                    rgb[v * 3 + 0] = c[3 * k + 0];
+                    rgb[v * 3 + 1] = c[3 * k + 1];
+                    rgb[v * 3 + 2] = c[3 * k + 2];
+                }
+            }
+        }
+    }
+}
+
+// K6: colorsAndDistances[i] = sdf(points[i])  (Sdf.cs:8).  xyz: n*3 floats, rgbd: n*4 floats.
+extern "C" __global__ void __launch_bounds__(256)
+sdfk_k_eval(const float* __restrict__ xyz, float* __restrict__ rgbd, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const sk_float4 r = sdf_eval(sk_make3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+        reinterpret_cast<float4*>(rgbd)[i] = make_float4(r.x, r.y, r.z, r.w);
+    }
+}
+
+struct sdfk_render_params {
+    int w, h;                  // full image size
+    int row_begin, row_end;    // rows rendered by this call (row band, RayMarcher.cs:50-61)
+    float cam[3];              // camera position = translation of inverse(view)   (RayMarcher.cs:97-99)
+    float ivp[16];             // inverse(view * projection), row-major             (RayMarcher.cs:107-108)
+    float nearp, farp;
+    int iters;
+};
+
+// Ray through pixel (i,j): RayMarcher.GetCameraRays per-pixel part (RayMarcher.cs:111-125)
+static __device__ __forceinline__ sk_float3 sdfk_ray_dir(const sdfk_render_params& P, int i, int j)
+{
+    const float y = 1.0f - 2.0f * (float)j / (float)(P.h - 1);
+    const float x = -1.0f + 2.0f * (float)i / (float)(P.w - 1);
+    // Vector4.Transform((x, y, 0, 1), ivp): ((x*m1 + y*m2) + 0*m3) + 1*m4
+    const float tx = x * P.ivp[0] + y * P.ivp[4] + 0.0f * P.ivp[8] + 1.0f * P.ivp[12];
+    const float ty = x * P.ivp[1] + y * P.ivp[5] + 0.0f * P.ivp[9] + 1.0f * P.ivp[13];
+    const float tz = x * P.ivp[2] + y * P.ivp[6] + 0.0f * P.ivp[10] + 1.0f * P.ivp[14];
+    const float tw = x * P.ivp[3] + y * P.ivp[7] + 0.0f * P.ivp[11] + 1.0f * P.ivp[15];
+    const float dx = tx / tw - P.cam[0], dy = ty / tw - P.cam[1], dz = tz / tw - P.cam[2];
+    const float len = sk_sqrt((dx * dx + dy * dy) + dz * dz);      // Vector3.Normalize = v / v.Length()
+    return sk_make3(dx / len, dy / len, dz / len);
+}
+
+// One thread per pixel; the reference's ~12 full-image temporaries per iteration live in registers.
+extern "C" __global__ void __launch_bounds__(128)
+sdfk_k_render(const sdfk_render_params P, float* __restrict__ rgb)
+{
+    const long long npix = (long long)(P.row_end - P.row_begin) * P.w;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+        const int j = P.row_begin + (int)(pix / P.w);
+        const int i = (int)(pix % P.w);
+        const sk_float3 rd = sdfk_ray_dir(P, i, j);
+        float depth = P.nearp - 0.1f;                              // RayMarcher.cs:136
+        float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+        for (int it = 0; it < P.iters; it++) {                     // fixed count, no early out (RayMarcher.cs:138-145)
+            const sk_float4 s = sdf_eval(sk_make3(rd.x * depth + P.cam[0], rd.y * depth + P.cam[1], rd.z * depth + P.cam[2]));
+            depth = depth + s.w;
+            if (it == P.iters - 1) { cr = cr + s.x; cg = cg + s.y; cb = cb + s.z; }
+        }
+        const float sx = P.cam[0] + rd.x * depth, sy = P.cam[1] + rd.y * depth, sz = P.cam[2] + rd.z * depth;
+        // DistanceGradient: taps +x,+y,+z,-x,-y,-z at GradOffset = 1e-5 (RayMarcher.cs:29,164-204)
+        const float go = 1e-5f;
+        const float px = sdf_eval(sk_make3(sx + go * 1.0f, sy + go * 0.0f, sz + go * 0.0f)).w;
+        const float py = sdf_eval(sk_make3(sx + go * 0.0f, sy + go * 1.0f, sz + go * 0.0f)).w;
+        const float pz = sdf_eval(sk_make3(sx + go * 0.0f, sy + go * 0.0f, sz + go * 1.0f)).w;
+        const float mx = sdf_eval(sk_make3(sx + -go * 1.0f, sy + -go * 0.0f, sz + -go * 0.0f)).w;
+        const float my = sdf_eval(sk_make3(sx + -go * 0.0f, sy + -go * 1.0f, sz + -go * 0.0f)).w;
+        const float mz = sdf_eval(sk_make3(sx + -go * 0.0f, sy + -go * 0.0f, sz + -go * 1.0f)).w;
+        float nx = px - mx, ny = py - my, nz = pz - mz;
+        const float nl = sk_sqrt(nx * nx + ny * ny + nz * nz);     // NormalizeInplace (VectorData.cs:490-510)
+        if (nl > 0.0f) { const float r = 1.0f / nl; nx = nx * r; ny = ny * r; nz = nz * r; }
+        float lx = 5.0f - sx, ly = 5.0f - sy, lz = 10.0f - sz;     // light (5,5,10) (RayMarcher.cs:149-150)
+        const float ll = sk_sqrt(lx * lx + ly * ly + lz * lz);
+        if (ll > 0.0f) { const float r = 1.0f / ll; lx = lx * r; ly = ly * r; lz = lz * r; }
+        float dv = nx * lx + ny * ly + nz * lz;                    // Dot (VectorData.cs:464-475)
+        dv = (dv != dv) ? dv : ((dv > 0.0f) ? dv : 0.0f);          // MaxInplace(0): MathF.Max, NaN propagates
+        const float mask = depth > P.farp ? 1.0f : 0.0f;           // bgMask (RayMarcher.cs:156)
+        const float notmask = mask == 0.0f ? 1.0f : 0.0f;
+        // fg = (dv*colour + 0.1) * notmask + mask*bg ; frag(=0) += fg  (RayMarcher.cs:154-160)
+        const float r0 = 0.0f + ((dv * cr + 0.1f) * notmask + mask * 0.5f);
+        const float g0 = 0.0f + ((dv * cg + 0.1f) * notmask + mask * 0.75f);
+        const float b0 = 0.0f + ((dv * cb + 0.1f) * notmask + mask * 1.0f);
+        rgb[pix * 3 + 0] = r0;
+        rgb[pix * 3 + 1] = g0;
+        rgb[pix * 3 + 2] = b0;
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+sdfk_k_render_depth(const sdfk_render_params P, float* __restrict__ depth_out)
+{
+    const long long npix = (long long)(P.row_end - P.row_begin) * P.w;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+        const int j = P.row_begin + (int)(pix / P.w);
+        const int i = (int)(pix % P.w);
+        const sk_float3 rd = sdfk_ray_dir(P, i, j);
+        float depth = P.nearp - 0.1f;
+        for (int it = 0; it < P.iters; it++) {
+            const sk_float4 s = sdf_eval(sk_make3(rd.x * depth + P.cam[0], rd.y * depth + P.cam[1], rd.z * depth + P.cam[2]));
+            depth = depth + s.w;
+        }
+        depth_out[pix] = depth;
+    }
+}

@@ -1,0 +1,889 @@
+// mc_kernels.cu -- Lewiner marching cubes on the GPU, order-exact with the reference's sequential
+// implementation (SdfKit/MarchingCubes.cs:39-546, SdfKit/Cell.cs:130-549).  Compiled for sm_100a with
+// -fmad=false: every FP64/FP32 decision and interpolation is the IEEE operation the CPU path performs.
+//
+// The reference numbers vertices by "first touch" while visiting cells z-outer / y / x-inner and walking
+// each cell's tiling row left to right, de-duplicating through two rolling face layers.  Every tiling row
+// references exactly the sign-changing edges of its cube (+ optionally the centre vertex), so first touch
+// is a pure function of geometry (DESIGN.md "order-exact formulation"):
+//   * the creator ("owner") of a grid-edge vertex is the sharing cell smallest in (k, j, i);
+//   * its id is  vbase[owner] + rank of the edge among the owner's created vertices in row order,
+//     vbase = exclusive prefix sum of per-cell created-vertex counts in visiting order;
+//   * triangle t of a cell is row entries 3t..3t+2 at  tbase[cell] + t.
+// Pipeline (one pass over the distance field, everything else is O(active cells)):
+//   K2 mc_classify  dist -> per 128-cell chunk packed counts (active, vertices, triangles)
+//   K3 mc_scan      warp-shuffle + decoupled look-back exclusive scan of the chunk counts
+//   K4a mc_compact  active chunks -> one McRecord per active cell, in visiting order
+//   K4b mc_emit     per record: triangle indices, created vertices (position, colour), normals gathered
+//                   in the reference's accumulation order, -normalize, Mesh.Transform, AABB
+#include <cstdio>
+
+#include "mc_kernels.cuh"
+#include "mc_luts.h"
+
+#define MC_EPS 0.0000001                       // FLT_EPSILON of MarchingCubes.cs:37 / Cell.cs:65
+#define MC_AMBIG 0x80000000u
+#define MC_LEAF(off, nt, center) ((unsigned)(off) | ((unsigned)(nt) << 14) | ((unsigned)(center) << 18))
+#define MC_LEAF_OFF(l) ((l) & 0x3FFFu)
+#define MC_LEAF_NT(l) (((l) >> 14) & 0xFu)
+#define MC_LEAF_CENTER(l) (((l) >> 18) & 1u)
+#define FULL 0xFFFFFFFFu
+
+static const signed char h_lut[MCL_BLOB_SIZE] = MCL_BLOB_INIT;
+__device__ const signed char d_lut[MCL_BLOB_SIZE] = MCL_BLOB_INIT;
+__device__ unsigned d_leaf[256];               // unambiguous cube index -> leaf, else MC_AMBIG
+__device__ unsigned short d_cross[256];        // cube index -> 12-bit mask of sign-changing edges
+
+// edge -> corner pair (Luts.cs:26-28 in corner numbering; MarchingCubes.cs:70-71)
+__host__ __device__ static inline void mc_edge_corners(int e, int& a, int& b)
+{
+    const int A[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
+    const int B[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+    a = A[e];
+    b = B[e];
+}
+
+cudaError_t mc_init_tables()
+{
+    unsigned leaf[256];
+    unsigned short cross[256];
+    // unambiguous Lewiner cases: tiling table offset, row length, triangle count (MarchingCubes.cs:98-372)
+    struct { int cas, off, len, nt; } simple[] = {
+        {1, MCL_tiling1, 3, 1}, {2, MCL_tiling2, 6, 2}, {5, MCL_tiling5, 9, 3}, {8, MCL_tiling8, 6, 2},
+        {9, MCL_tiling9, 12, 4}, {11, MCL_tiling11, 12, 4}, {14, MCL_tiling14, 12, 4}};
+    for (int idx = 0; idx < 256; idx++) {
+        int cas = h_lut[MCL_cases + idx * 2], cfg = h_lut[MCL_cases + idx * 2 + 1];
+        leaf[idx] = (cas == 0) ? 0u : MC_AMBIG;
+        for (auto& s : simple)
+            if (s.cas == cas) leaf[idx] = MC_LEAF(s.off + cfg * s.len, s.nt, 0);
+        unsigned m = 0;
+        for (int e = 0; e < 12; e++) {
+            int a, b;
+            mc_edge_corners(e, a, b);
+            if (((idx >> a) ^ (idx >> b)) & 1) m |= 1u << e;
+        }
+        cross[idx] = (unsigned short)m;
+    }
+    cudaError_t err = cudaMemcpyToSymbol(d_leaf, leaf, sizeof(leaf));
+    if (err != cudaSuccess) return err;
+    return cudaMemcpyToSymbol(d_cross, cross, sizeof(cross));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lewiner disambiguation (FP64, no contraction)
+// ---------------------------------------------------------------------------------------------------
+
+// MarchingCubes.TestFace (MarchingCubes.cs:376-407)
+__device__ static bool mc_test_face(const double* v, int face)
+{
+    const int af = face < 0 ? -face : face;
+    double A = 0.0, B = 0.0, C = 0.0, D = 0.0;
+    switch (af) {
+    case 1: A = v[0]; B = v[4]; C = v[5]; D = v[1]; break;
+    case 2: A = v[1]; B = v[5]; C = v[6]; D = v[2]; break;
+    case 3: A = v[2]; B = v[6]; C = v[7]; D = v[3]; break;
+    case 4: A = v[3]; B = v[7]; C = v[4]; D = v[0]; break;
+    case 5: A = v[0]; B = v[3]; C = v[2]; D = v[1]; break;
+    case 6: A = v[4]; B = v[7]; C = v[6]; D = v[5]; break;
+    }
+    const double acbd = A * C - B * D;
+    if (acbd > -MC_EPS && acbd < MC_EPS) return face >= 0;
+    return (double)face * A * acbd >= 0;
+}
+
+// MarchingCubes.TestInternal (MarchingCubes.cs:412-546)
+__device__ static bool mc_test_internal(const double* v, int cas, int cfg, int sub, int s)
+{
+    double t, At = 0.0, Bt = 0.0, Ct = 0.0, Dt = 0.0;
+    if (cas == 4 || cas == 10) {
+        const double a = (v[4] - v[0]) * (v[6] - v[2]) - (v[7] - v[3]) * (v[5] - v[1]);
+        const double b = v[2] * (v[4] - v[0]) + v[0] * (v[6] - v[2]) - v[1] * (v[7] - v[3]) - v[3] * (v[5] - v[1]);
+        t = -b / (2 * a + MC_EPS);
+        if (t < 0 || t > 1) return s > 0;
+        At = v[0] + (v[4] - v[0]) * t;
+        Bt = v[3] + (v[7] - v[3]) * t;
+        Ct = v[2] + (v[6] - v[2]) * t;
+        Dt = v[1] + (v[5] - v[1]) * t;
+    } else {
+        int edge;
+        if (cas == 6) edge = d_lut[MCL_test6 + cfg * 3 + 2];
+        else if (cas == 7) edge = d_lut[MCL_test7 + cfg * 5 + 4];
+        else if (cas == 12) edge = d_lut[MCL_test12 + cfg * 4 + 3];
+        else edge = d_lut[MCL_tiling13_5_1 + (cfg * 4 + sub) * 18];
+        if (edge >= 0 && edge < 12) {
+            // reference edge e runs a->b; the three opposite edges, interpolated at the same parameter,
+            // are given as (from,to) corner pairs for Bt, Ct, Dt (MarchingCubes.cs:440-511), 3 bits each
+            const unsigned tab[12] = {
+                // a | b<<3 | B0<<6 | B1<<9 | C0<<12 | C1<<15 | D0<<18 | D1<<21
+                0u | 1u << 3 | 3u << 6 | 2u << 9 | 7u << 12 | 6u << 15 | 4u << 18 | 5u << 21,
+                1u | 2u << 3 | 0u << 6 | 3u << 9 | 4u << 12 | 7u << 15 | 5u << 18 | 6u << 21,
+                2u | 3u << 3 | 1u << 6 | 0u << 9 | 5u << 12 | 4u << 15 | 6u << 18 | 7u << 21,
+                3u | 0u << 3 | 2u << 6 | 1u << 9 | 6u << 12 | 5u << 15 | 7u << 18 | 4u << 21,
+                4u | 5u << 3 | 7u << 6 | 6u << 9 | 3u << 12 | 2u << 15 | 0u << 18 | 1u << 21,
+                5u | 6u << 3 | 4u << 6 | 7u << 9 | 0u << 12 | 3u << 15 | 1u << 18 | 2u << 21,
+                6u | 7u << 3 | 5u << 6 | 4u << 9 | 1u << 12 | 0u << 15 | 2u << 18 | 3u << 21,
+                7u | 4u << 3 | 6u << 6 | 5u << 9 | 2u << 12 | 1u << 15 | 3u << 18 | 0u << 21,
+                0u | 4u << 3 | 3u << 6 | 7u << 9 | 2u << 12 | 6u << 15 | 1u << 18 | 5u << 21,
+                1u | 5u << 3 | 0u << 6 | 4u << 9 | 3u << 12 | 7u << 15 | 2u << 18 | 6u << 21,
+                2u | 6u << 3 | 1u << 6 | 5u << 9 | 0u << 12 | 4u << 15 | 3u << 18 | 7u << 21,
+                3u | 7u << 3 | 2u << 6 | 6u << 9 | 1u << 12 | 5u << 15 | 0u << 18 | 4u << 21};
+            const unsigned r = tab[edge];
+#define TC(n) v[(r >> (3 * (n))) & 7u]
+            t = TC(0) / (TC(0) - TC(1) + MC_EPS);
+            At = 0;
+            Bt = TC(2) + (TC(3) - TC(2)) * t;
+            Ct = TC(4) + (TC(5) - TC(4)) * t;
+            Dt = TC(6) + (TC(7) - TC(6)) * t;
+#undef TC
+        }
+    }
+    int test = 0;
+    if (At >= 0) test += 1;
+    if (Bt >= 0) test += 2;
+    if (Ct >= 0) test += 4;
+    if (Dt >= 0) test += 8;
+    switch (test) {
+    case 5: if (At * Ct - Bt * Dt < MC_EPS) return s > 0; break;
+    case 10: if (At * Ct - Bt * Dt >= MC_EPS) return s > 0; break;
+    case 7: case 11: case 13: case 14: case 15: return s < 0;
+    default: return s > 0;
+    }
+    return s < 0;
+}
+
+#define LEAF2(name, cfg, nt, center) MC_LEAF(MCL_##name + (cfg) * MCL_##name##_D1, nt, center)
+#define LEAF3(name, cfg, sub, nt, center) MC_LEAF(MCL_##name + ((cfg) * MCL_##name##_D1 + (sub)) * MCL_##name##_D2, nt, center)
+
+// MarchingCubes.TheBigSwitch for the ambiguous cases (MarchingCubes.cs:105-366): chooses the tiling row.
+// v[k] = (double)value_k - (double)iso in the reference's corner numbering.
+__device__ __noinline__ static unsigned mc_resolve(int idx, const double* v)
+{
+    const int cas = d_lut[MCL_cases + idx * 2];
+    const int cfg = d_lut[MCL_cases + idx * 2 + 1];
+    int sub = 0;
+    switch (cas) {
+    case 3:
+        return mc_test_face(v, d_lut[MCL_test3 + cfg]) ? LEAF2(tiling3_2, cfg, 4, 0) : LEAF2(tiling3_1, cfg, 2, 0);
+    case 4:
+        return mc_test_internal(v, cas, cfg, 0, d_lut[MCL_test4 + cfg]) ? LEAF2(tiling4_1, cfg, 2, 0) : LEAF2(tiling4_2, cfg, 6, 0);
+    case 6:
+        if (mc_test_face(v, d_lut[MCL_test6 + cfg * 3])) return LEAF2(tiling6_2, cfg, 5, 0);
+        return mc_test_internal(v, cas, cfg, 0, d_lut[MCL_test6 + cfg * 3 + 1]) ? LEAF2(tiling6_1_1, cfg, 3, 0) : LEAF2(tiling6_1_2, cfg, 9, 1);
+    case 7:
+        if (mc_test_face(v, d_lut[MCL_test7 + cfg * 5 + 0])) sub += 1;
+        if (mc_test_face(v, d_lut[MCL_test7 + cfg * 5 + 1])) sub += 2;
+        if (mc_test_face(v, d_lut[MCL_test7 + cfg * 5 + 2])) sub += 4;
+        switch (sub) {
+        case 0: return LEAF2(tiling7_1, cfg, 3, 0);
+        case 1: return LEAF3(tiling7_2, cfg, 0, 5, 0);
+        case 2: return LEAF3(tiling7_2, cfg, 1, 5, 0);
+        case 3: return LEAF3(tiling7_3, cfg, 0, 9, 1);
+        case 4: return LEAF3(tiling7_2, cfg, 2, 5, 0);
+        case 5: return LEAF3(tiling7_3, cfg, 1, 9, 1);
+        case 6: return LEAF3(tiling7_3, cfg, 2, 9, 1);
+        default:
+            return mc_test_internal(v, cas, cfg, sub, d_lut[MCL_test7 + cfg * 5 + 3]) ? LEAF2(tiling7_4_2, cfg, 9, 0) : LEAF2(tiling7_4_1, cfg, 5, 0);
+        }
+    case 10:
+    case 12: {
+        const int tst = (cas == 10) ? MCL_test10 + cfg * 3 : MCL_test12 + cfg * 4;
+        const bool f0 = mc_test_face(v, d_lut[tst]);
+        const bool f1 = mc_test_face(v, d_lut[tst + 1]);
+        if (cas == 10) {
+            if (f0) return f1 ? LEAF2(tiling10_1_1_, cfg, 4, 0) : LEAF2(tiling10_2, cfg, 8, 1);
+            if (f1) return LEAF2(tiling10_2_, cfg, 8, 1);
+            return mc_test_internal(v, cas, cfg, 0, d_lut[tst + 2]) ? LEAF2(tiling10_1_1, cfg, 4, 0) : LEAF2(tiling10_1_2, cfg, 8, 0);
+        }
+        if (f0) return f1 ? LEAF2(tiling12_1_1_, cfg, 4, 0) : LEAF2(tiling12_2, cfg, 8, 1);
+        if (f1) return LEAF2(tiling12_2_, cfg, 8, 1);
+        return mc_test_internal(v, cas, cfg, 0, d_lut[tst + 2]) ? LEAF2(tiling12_1_1, cfg, 4, 0) : LEAF2(tiling12_1_2, cfg, 8, 0);
+    }
+    case 13: {
+        for (int k = 0; k < 6; k++)
+            if (mc_test_face(v, d_lut[MCL_test13 + cfg * 7 + k])) sub += 1 << k;
+        sub = d_lut[MCL_subconfig13 + sub];
+        if (sub == 0) return LEAF2(tiling13_1, cfg, 4, 0);
+        if (sub <= 6) return LEAF3(tiling13_2, cfg, sub - 1, 6, 0);
+        if (sub <= 18) return LEAF3(tiling13_3, cfg, sub - 7, 10, 1);
+        if (sub <= 22) return LEAF3(tiling13_4, cfg, sub - 19, 12, 1);
+        if (sub <= 26) {
+            const int s5 = sub - 23;
+            return mc_test_internal(v, cas, cfg, s5, d_lut[MCL_test13 + cfg * 7 + 6]) ? LEAF3(tiling13_5_1, cfg, s5, 6, 0)
+                                                                                      : LEAF3(tiling13_5_2, cfg, s5, 10, 0);
+        }
+        if (sub <= 38) return LEAF3(tiling13_3_, cfg, sub - 27, 10, 1);
+        if (sub <= 44) return LEAF3(tiling13_2_, cfg, sub - 39, 6, 0);
+        if (sub == 45) return LEAF2(tiling13_1_, cfg, 4, 0);
+        return MC_LEAF(0, 0, 0);   // "Impossible case 13?" (MarchingCubes.cs:365): no triangles
+    }
+    }
+    return MC_LEAF(0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// geometry helpers
+// ---------------------------------------------------------------------------------------------------
+
+// Which of a cell's 13 vertex slots it creates itself (first touch in visiting order); kg = GLOBAL layer.
+__device__ static inline unsigned mc_owned_mask(int i, int j, int kg)
+{
+    unsigned m = (1u << 5) | (1u << 6) | (1u << 10) | (1u << 12);
+    if (j == 0) m |= (1u << 4) | (1u << 9);
+    if (i == 0) m |= (1u << 7) | (1u << 11);
+    if (i == 0 && j == 0) m |= 1u << 8;
+    if (kg == 0) {
+        m |= (1u << 1) | (1u << 2);
+        if (j == 0) m |= 1u << 0;
+        if (i == 0) m |= 1u << 3;
+    }
+    return m;
+}
+
+__device__ static inline size_t mc_vox(const McGrid& g, int i, int j, int kg, int dx, int dy, int dz)
+{
+    const int x = (i + dx) * g.step, y = (j + dy) * g.step, zl = (kg + dz) * g.step - g.z0;
+    return ((size_t)zl * g.ny + y) * (size_t)g.nx + x;
+}
+
+// values of the 8 cube corners minus iso, as doubles, reference corner numbering (Cell.cs:206-213)
+__device__ static inline void mc_load_cell(const McGrid& g, const float* __restrict__ dist, int i, int j, int kg, double* v)
+{
+    const double iso = (double)g.iso;
+    v[0] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 0, 0)) - iso;
+    v[1] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 0, 0)) - iso;
+    v[2] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 1, 0)) - iso;
+    v[3] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 1, 0)) - iso;
+    v[4] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 0, 1)) - iso;
+    v[5] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 0, 1)) - iso;
+    v[6] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 1, 1)) - iso;
+    v[7] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 1, 1)) - iso;
+}
+
+__device__ static inline int mc_index_of(const double* v)   // Cell.cs:219-229: strict > 0
+{
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (v[k] > 0.0) idx |= 1 << k;
+    return idx;
+}
+
+// leaf + created-vertex count of an active cell
+__device__ __noinline__ static unsigned mc_resolve_cell(const McGrid& g, const float* __restrict__ dist, int idx, int i, int j, int kg)
+{
+    double v[8];
+    mc_load_cell(g, dist, i, j, kg, v);
+    return mc_resolve(idx, v);
+}
+
+__device__ static inline unsigned mc_cell_leaf(const McGrid& g, const float* __restrict__ dist, int idx, int i, int j, int kg)
+{
+    unsigned leaf = d_leaf[idx];
+    if (leaf & MC_AMBIG) leaf = mc_resolve_cell(g, dist, idx, i, j, kg);
+    return leaf;
+}
+
+__device__ static inline unsigned mc_cell_counts(unsigned leaf, int idx, int i, int j, int kg)
+{
+    const unsigned nv = __popc((unsigned)d_cross[idx] & mc_owned_mask(i, j, kg)) + MC_LEAF_CENTER(leaf);
+    return MC_CNT_PACK(1, nv, MC_LEAF_NT(leaf));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 mc_classify: one warp marches a 128-cell x-chunk by MC_R rows through MC_K layers; every voxel's
+// sign is computed once per march (x/y/z halos aside) and only packed per-chunk counts are written.
+// ---------------------------------------------------------------------------------------------------
+#define MC_R 8
+#define MC_K 16
+#define MC_CLASSIFY_WARPS 8
+
+// 5 sign bits for voxels (i0..i0+4)*step of voxel row (y, zl): bit t = value > iso (strict, Cell.cs:221-228;
+// float compare is exact for (double)value - (double)iso > 0)
+template <bool VEC>
+__device__ static inline unsigned mc_row_signs(const McGrid& g, const float* __restrict__ dist, int i0, int y, int zl, unsigned lane)
+{
+    const float* row = dist + ((size_t)zl * g.ny + y) * (size_t)g.nx;
+    unsigned s = 0;
+    if (VEC) {   // step == 1, nx % 4 == 0: one 16-byte load per lane, neighbour bit by shuffle
+        if (i0 < g.nx) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(row + i0));
+            s = (q.x > g.iso ? 1u : 0u) | (q.y > g.iso ? 2u : 0u) | (q.z > g.iso ? 4u : 0u) | (q.w > g.iso ? 8u : 0u);
+        }
+        unsigned nb = __shfl_down_sync(FULL, s, 1) & 1u;
+        if (lane == 31) nb = (i0 + 4 < g.nx) ? (__ldg(row + i0 + 4) > g.iso ? 1u : 0u) : 0u;
+        s |= nb << 4;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            const long long x = (long long)(i0 + t) * g.step;
+            if (x < g.nx && __ldg(row + x) > g.iso) s |= 1u << t;
+        }
+    }
+    return s;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(MC_CLASSIFY_WARPS * 32)
+mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
+                   unsigned njb, unsigned nkb, unsigned ntiles)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gw = blockIdx.x * MC_CLASSIFY_WARPS + (threadIdx.x >> 5);
+    const unsigned nw = gridDim.x * MC_CLASSIFY_WARPS;
+    for (unsigned tile = gw; tile < ntiles; tile += nw) {
+        // tile -> (xc fastest, then row block, then layer block): neighbouring warps read neighbouring segments
+        const unsigned xc = tile % (unsigned)g.cpr;
+        const unsigned t2 = tile / (unsigned)g.cpr;
+        const unsigned jb = t2 % njb;
+        const unsigned kb = t2 / njb;
+        const int i0 = (int)(xc * 128u + lane * 4u);
+        const int j0 = (int)(jb * MC_R);
+        const int kl0 = (int)(kb * MC_K);                     // local layer index
+        const int nrows = min(MC_R, g.ncy - j0);
+        const int nlay = min(MC_K, g.nk - kl0);
+
+        unsigned prev[MC_R + 1], cur[MC_R + 1];
+        {
+            const int zl = (g.k0 + kl0) * g.step - g.z0;
+#pragma unroll
+            for (int r = 0; r <= MC_R; r++)
+                prev[r] = (r <= nrows) ? mc_row_signs<VEC>(g, dist, i0, (j0 + r) * g.step, zl, lane) : 0u;
+        }
+        for (int kk = 0; kk < nlay; kk++) {
+            const int kg = g.k0 + kl0 + kk;
+            const int zl = (kg + 1) * g.step - g.z0;
+#pragma unroll
+            for (int r = 0; r <= MC_R; r++)
+                cur[r] = (r <= nrows) ? mc_row_signs<VEC>(g, dist, i0, (j0 + r) * g.step, zl, lane) : 0u;
+#pragma unroll
+            for (int r = 0; r < MC_R; r++) {
+                if (r < nrows) {
+                    const unsigned lo0 = prev[r], lo1 = prev[r + 1], hi0 = cur[r], hi1 = cur[r + 1];
+                    unsigned cnt = 0;
+                    const unsigned any = lo0 | lo1 | hi0 | hi1, all = lo0 & lo1 & hi0 & hi1;
+                    if (any != 0u && all != 31u) {
+                        const int j = j0 + r;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const int idx = (int)(((lo0 >> c) & 3u) | (((lo1 >> (c + 1)) & 1u) << 2) | (((lo1 >> c) & 1u) << 3) |
+                                                  (((hi0 >> c) & 3u) << 4) | (((hi1 >> (c + 1)) & 1u) << 6) | (((hi1 >> c) & 1u) << 7));
+                            const int i = i0 + c;
+                            if (i < g.ncx && idx != 0 && idx != 255) {
+                                const unsigned leaf = mc_cell_leaf(g, dist, idx, i, j, kg);
+                                cnt += mc_cell_counts(leaf, idx, i, j, kg);
+                            }
+                        }
+                    }
+                    const unsigned total = __reduce_add_sync(FULL, cnt);
+                    if (lane == 0) counts[((size_t)(kl0 + kk) * g.ncy + (j0 + r)) * g.cpr + xc] = total;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r <= MC_R; r++) prev[r] = cur[r];
+        }
+    }
+}
+
+cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s)
+{
+    if (g.nchunks == 0) return cudaSuccess;
+    const unsigned njb = (g.ncy + MC_R - 1) / MC_R, nkb = (g.nk + MC_K - 1) / MC_K;
+    const unsigned long long nt = (unsigned long long)g.cpr * njb * nkb;
+    if (nt > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    const unsigned ntiles = (unsigned)nt;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned blocks = (ntiles + MC_CLASSIFY_WARPS - 1) / MC_CLASSIFY_WARPS;
+    const unsigned maxb = (unsigned)sms * 8u;
+    if (blocks > maxb) blocks = maxb;
+    const bool vec = g.step == 1 && (g.nx & 3) == 0;
+    if (vec) mc_classify_kernel<true><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
+    else mc_classify_kernel<false><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3 mc_scan: exclusive prefix sums (records, vertices, triangles) over the chunk counts, in visiting
+// order.  Single pass: warp-shuffle scans inside a tile, decoupled look-back between tiles.
+// ---------------------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+struct ScanWs {
+    unsigned ticket;
+    unsigned pad[3];
+    uint4 desc[1];   // status (0 none, 1 aggregate, 2 inclusive), act, verts, tris -- one 16-byte word per tile
+};
+
+size_t mc_scan_workspace_bytes(unsigned nchunks)
+{
+    const size_t ntiles = ((size_t)nchunks + SCAN_TILE - 1) / SCAN_TILE;
+    return 16 + (ntiles + 1) * sizeof(uint4);
+}
+
+__device__ static inline uint4 ld_desc(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ static inline void st_desc(uint4* p, uint4 v)
+{
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, unsigned n, ScanWs* ws, McTotals* totals)
+{
+    __shared__ unsigned s_tile;
+    __shared__ uint3 s_warp[SCAN_THREADS / 32];
+    __shared__ uint3 s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ws->ticket, 1u);   // tiles start in order: look-back cannot deadlock
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned first = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+
+    unsigned c[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) c[k] = (first + k < n) ? counts[first + k] : 0u;
+    uint3 sum = make_uint3(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { sum.x += MC_CNT_ACT(c[k]); sum.y += MC_CNT_V(c[k]); sum.z += MC_CNT_T(c[k]); }
+    // inclusive warp scan
+    uint3 inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned x = __shfl_up_sync(FULL, inc.x, d), y = __shfl_up_sync(FULL, inc.y, d), z = __shfl_up_sync(FULL, inc.z, d);
+        if (lane >= (unsigned)d) { inc.x += x; inc.y += y; inc.z += z; }
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint3 woff = make_uint3(0, 0, 0), agg = make_uint3(0, 0, 0);
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        const uint3 t = s_warp[w];
+        if ((unsigned)w < warp) { woff.x += t.x; woff.y += t.y; woff.z += t.z; }
+        agg.x += t.x; agg.y += t.y; agg.z += t.z;
+    }
+    // decoupled look-back by warp 0
+    if (warp == 0) {
+        uint3 excl = make_uint3(0, 0, 0);
+        if (tile > 0) {
+            if (lane == 0) st_desc(&ws->desc[tile], make_uint4(1u, agg.x, agg.y, agg.z));
+            int pred = (int)tile - 1;
+            for (;;) {
+                const int t = pred - (int)lane;
+                uint4 d = make_uint4(2u, 0, 0, 0);           // tiles before the first: inclusive prefix 0
+                if (t >= 0) {
+                    do { d = ld_desc(&ws->desc[t]); } while (d.x == 0u);
+                }
+                const unsigned incl_mask = __ballot_sync(FULL, d.x == 2u);
+                const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+                uint3 part = ((int)lane <= stop) ? make_uint3(d.y, d.z, d.w) : make_uint3(0, 0, 0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    part.x += __shfl_xor_sync(FULL, part.x, o);
+                    part.y += __shfl_xor_sync(FULL, part.y, o);
+                    part.z += __shfl_xor_sync(FULL, part.z, o);
+                }
+                excl.x += part.x; excl.y += part.y; excl.z += part.z;
+                if (incl_mask) break;
+                pred -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_desc(&ws->desc[tile], make_uint4(2u, excl.x + agg.x, excl.y + agg.y, excl.z + agg.z));
+            s_excl = excl;
+            if ((unsigned long long)(tile + 1) * SCAN_TILE >= n) {   // last tile: totals
+                totals->nact = excl.x + agg.x;
+                totals->nverts = excl.y + agg.y;
+                totals->ntris = excl.z + agg.z;
+            }
+        }
+    }
+    __syncthreads();
+    const uint3 te = s_excl;
+    uint3 run = make_uint3(te.x + woff.x + inc.x - sum.x, te.y + woff.y + inc.y - sum.y, te.z + woff.z + inc.z - sum.z);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (first + k < n) base[first + k] = make_uint4(run.x, run.y, run.z, c[k]);
+        run.x += MC_CNT_ACT(c[k]); run.y += MC_CNT_V(c[k]); run.z += MC_CNT_T(c[k]);
+    }
+}
+
+cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
+                           McTotals* totals, cudaStream_t s)
+{
+    cudaError_t err = cudaMemsetAsync(totals, 0, sizeof(McTotals), s);
+    if (err != cudaSuccess || nchunks == 0) return err;
+    if (ws_bytes < mc_scan_workspace_bytes(nchunks)) return cudaErrorInvalidValue;
+    err = cudaMemsetAsync(scan_ws, 0, mc_scan_workspace_bytes(nchunks), s);
+    if (err != cudaSuccess) return err;
+    const unsigned ntiles = (nchunks + SCAN_TILE - 1) / SCAN_TILE;
+    mc_scan_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(counts, base, nchunks, (ScanWs*)scan_ws, totals);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4a mc_compact: re-classify the active chunks and write one record per active cell, in visiting order
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned* __restrict__ counts,
+                  const uint4* __restrict__ base, McRecord* __restrict__ recs)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned c0 = gw * 32u; c0 < g.nchunks; c0 += nw * 32u) {
+        const unsigned mine = (c0 + lane < g.nchunks) ? MC_CNT_ACT(counts[c0 + lane]) : 0u;
+        unsigned todo = __ballot_sync(FULL, mine != 0u);
+        while (todo) {
+            const unsigned chunk = c0 + (unsigned)(__ffs(todo) - 1);
+            todo &= todo - 1;
+            const unsigned xc = chunk % (unsigned)g.cpr;
+            const unsigned row = chunk / (unsigned)g.cpr;
+            const int j = (int)(row % (unsigned)g.ncy);
+            const int kl = (int)(row / (unsigned)g.ncy);
+            const int kg = g.k0 + kl;
+            const int i0 = (int)(xc * 128u + lane * 4u);
+            unsigned leaf[4];
+            unsigned cnt[4];
+            unsigned tot = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                leaf[c] = 0;
+                cnt[c] = 0;
+                const int i = i0 + c;
+                if (i < g.ncx) {
+                    double v[8];
+                    mc_load_cell(g, dist, i, j, kg, v);
+                    const int idx = mc_index_of(v);
+                    if (idx != 0 && idx != 255) {
+                        unsigned lf = d_leaf[idx];
+                        if (lf & MC_AMBIG) lf = mc_resolve(idx, v);
+                        leaf[c] = lf;
+                        cnt[c] = mc_cell_counts(lf, idx, i, j, kg);
+                    }
+                }
+                tot += cnt[c];
+            }
+            // exclusive warp scan of the packed (act | verts | tris) counts; fields cannot overflow inside a chunk
+            unsigned inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(FULL, inc, d);
+                if (lane >= (unsigned)d) inc += t;
+            }
+            unsigned run = inc - tot;
+            const uint4 b = base[chunk];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (cnt[c]) {
+                    McRecord r;
+                    r.cell = (unsigned)(i0 + c) + (unsigned)g.ncx * ((unsigned)j + (unsigned)g.ncy * (unsigned)kl);
+                    r.info = leaf[c];
+                    r.vbase = b.y + MC_CNT_V(run);
+                    r.tbase = b.z + MC_CNT_T(run);
+                    recs[b.x + MC_CNT_ACT(run)] = r;
+                    run += cnt[c];
+                }
+            }
+        }
+    }
+}
+
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+                              McRecord* recs, cudaStream_t s)
+{
+    if (g.nchunks == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned groups = (g.nchunks + 31u) / 32u;
+    unsigned blocks = (groups + 7u) / 8u;
+    if (blocks > (unsigned)sms * 8u) blocks = (unsigned)sms * 8u;
+    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, counts, base, recs);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4b mc_emit
+// ---------------------------------------------------------------------------------------------------
+
+// record of cell (i, j, kl) -- must exist
+__device__ static inline int mc_find_record(const McEmitParams& p, int i, int j, int kl)
+{
+    const McGrid& g = p.g;
+    const unsigned chunk = ((unsigned)kl * (unsigned)g.ncy + (unsigned)j) * (unsigned)g.cpr + ((unsigned)i >> 7);
+    const uint4 b = p.base[chunk];
+    const unsigned cell = (unsigned)i + (unsigned)g.ncx * ((unsigned)j + (unsigned)g.ncy * (unsigned)kl);
+    int lo = (int)b.x, hi = (int)(b.x + MC_CNT_ACT(b.w)) - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned c = p.recs[mid].cell;
+        if (c == cell) return mid;
+        if (c < cell) lo = mid + 1;
+        else hi = mid - 1;
+    }
+    return -1;
+}
+
+// position of slot e in the creation order of a cell: number of distinct created slots first seen before it
+__device__ static inline int mc_rank_in_row(const signed char* row, int nent, unsigned owned, int e)
+{
+    unsigned seen = 0;
+    int rank = 0;
+    for (int k = 0; k < nent; k++) {
+        const int q = row[k];
+        if (q == e) return rank;
+        const unsigned bit = 1u << q;
+        if ((owned & bit) && !(seen & bit)) { seen |= bit; rank++; }
+    }
+    return -1;
+}
+
+// (float) gradient row `r` (ORIGINAL corner numbering, Cell.cs:491-498) component a = v[p] - v[q]
+__device__ static inline double mc_vg(const double* v, int r, int a)
+{
+    // 8 rows x 3 components, (p,q) packed 3 bits each
+    const unsigned short tab[24] = {
+        0 | 1 << 3, 0 | 3 << 3, 0 | 4 << 3,    // corner 0
+        0 | 1 << 3, 1 | 2 << 3, 1 | 5 << 3,    // corner 1
+        3 | 2 << 3, 1 | 2 << 3, 2 | 6 << 3,    // corner 2
+        3 | 2 << 3, 0 | 3 << 3, 3 | 7 << 3,    // corner 3
+        4 | 5 << 3, 4 | 7 << 3, 0 | 4 << 3,    // corner 4
+        4 | 5 << 3, 5 | 6 << 3, 1 | 5 << 3,    // corner 5
+        7 | 6 << 3, 5 | 6 << 3, 2 | 6 << 3,    // corner 6
+        7 | 6 << 3, 4 | 7 << 3, 3 | 7 << 3};   // corner 7
+    const unsigned t = tab[r * 3 + a];
+    return v[t & 7u] - v[(t >> 3) & 7u];
+}
+
+struct McF3 { float x, y, z; };
+
+// adds, for `times` references of local edge e in a sharing cell, the two end-corner gradient contributions
+// exactly like Cell.AddGradientFromIndex (Cell.cs:154-158,331-333): note vg is indexed with the dz*4+dy*2+dx
+// corner index although its rows are in the v0..v7 numbering -- a quirk of the reference that is preserved.
+__device__ static inline void mc_add_edge_gradients(const double* v, int e, int times, McF3& n)
+{
+    const int dx1 = d_lut[MCL_edgesrelx + e * 2], dx2 = d_lut[MCL_edgesrelx + e * 2 + 1];
+    const int dy1 = d_lut[MCL_edgesrely + e * 2], dy2 = d_lut[MCL_edgesrely + e * 2 + 1];
+    const int dz1 = d_lut[MCL_edgesrelz + e * 2], dz2 = d_lut[MCL_edgesrelz + e * 2 + 1];
+    const int i1 = dz1 * 4 + dy1 * 2 + dx1, i2 = dz2 * 4 + dy2 * 2 + dx2;
+    const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};                     // vv[] re-ordering (Cell.cs:453-460)
+    const double w1 = 1.0 / (MC_EPS + fabs(v[ro[i1]]));
+    const double w2 = 1.0 / (MC_EPS + fabs(v[ro[i2]]));
+    const float g1x = (float)(mc_vg(v, i1, 0) * w1), g1y = (float)(mc_vg(v, i1, 1) * w1), g1z = (float)(mc_vg(v, i1, 2) * w1);
+    const float g2x = (float)(mc_vg(v, i2, 0) * w2), g2y = (float)(mc_vg(v, i2, 1) * w2), g2z = (float)(mc_vg(v, i2, 2) * w2);
+    for (int t = 0; t < times; t++) {
+        n.x = n.x + g1x; n.y = n.y + g1y; n.z = n.z + g1z;
+        n.x = n.x + g2x; n.y = n.y + g2y; n.z = n.z + g2z;
+    }
+}
+
+__device__ static inline unsigned mc_float_key(float f)   // monotonic float -> uint
+{
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ static inline void mc_store_vertex(const McEmitParams& p, long long slot, McF3 pos, McF3 col, McF3 nsum)
+{
+    // Cell.NegativeNormals (Cell.cs:97-109): -Vector3.Normalize(sum)
+    const float len = sqrtf((nsum.x * nsum.x + nsum.y * nsum.y) + nsum.z * nsum.z);
+    McF3 n = {-(nsum.x / len), -(nsum.y / len), -(nsum.z / len)};
+    if (p.has_xf) {   // Mesh.Transform (Mesh.cs:57-62)
+        const float* M = p.M;
+        const float* N = p.N;
+        const McF3 tp = {pos.x * M[0] + pos.y * M[4] + pos.z * M[8] + M[12], pos.x * M[1] + pos.y * M[5] + pos.z * M[9] + M[13],
+                         pos.x * M[2] + pos.y * M[6] + pos.z * M[10] + M[14]};
+        const McF3 tn = {n.x * N[0] + n.y * N[4] + n.z * N[8], n.x * N[1] + n.y * N[5] + n.z * N[9],
+                         n.x * N[2] + n.y * N[6] + n.z * N[10]};
+        const float l2 = sqrtf((tn.x * tn.x + tn.y * tn.y) + tn.z * tn.z);
+        pos = tp;
+        n.x = tn.x / l2; n.y = tn.y / l2; n.z = tn.z / l2;
+    }
+    float* vo = p.verts + slot * 3;
+    float* co = p.cols + slot * 3;
+    float* no = p.nrms + slot * 3;
+    vo[0] = pos.x; vo[1] = pos.y; vo[2] = pos.z;
+    co[0] = col.x; co[1] = col.y; co[2] = col.z;
+    no[0] = n.x; no[1] = n.y; no[2] = n.z;
+    // Mesh.Measure (Mesh.cs:30-45)
+    atomicMin(p.aabb_keys + 0, mc_float_key(pos.x));
+    atomicMin(p.aabb_keys + 1, mc_float_key(pos.y));
+    atomicMin(p.aabb_keys + 2, mc_float_key(pos.z));
+    atomicMax(p.aabb_keys + 3, mc_float_key(pos.x));
+    atomicMax(p.aabb_keys + 4, mc_float_key(pos.y));
+    atomicMax(p.aabb_keys + 5, mc_float_key(pos.z));
+}
+
+__global__ void __launch_bounds__(128)
+mc_emit_kernel(const McEmitParams p)
+{
+    const McGrid& g = p.g;
+    const unsigned r = p.rec_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.rec_end) return;
+    const McRecord rec = p.recs[r];
+    const int i = (int)(rec.cell % (unsigned)g.ncx);
+    const unsigned t2 = rec.cell / (unsigned)g.ncx;
+    const int j = (int)(t2 % (unsigned)g.ncy);
+    const int kl = (int)(t2 / (unsigned)g.ncy);
+    const int kg = g.k0 + kl;
+    const signed char* row = d_lut + MC_LEAF_OFF(rec.info);
+    const int nt = (int)MC_LEAF_NT(rec.info);
+    const int nent = 3 * nt;
+    const unsigned owned = mc_owned_mask(i, j, kg);
+
+    double v[8];
+    mc_load_cell(g, p.dist, i, j, kg, v);
+
+    // ---- vertex id of every slot this cell references
+    unsigned refd = 0;
+    for (int k = 0; k < nent; k++) refd |= 1u << row[k];
+    long long vid[13];
+    for (int e = 0; e < 13; e++) {
+        if (!((refd >> e) & 1u)) continue;
+        if ((owned >> e) & 1u) {
+            vid[e] = (long long)(rec.vbase + (unsigned)mc_rank_in_row(row, nent, owned, e));
+            continue;
+        }
+        // creator = sharing cell smallest in (k, j, i); e2 = the edge's id in the creator's numbering
+        int di = 0, dj = 0, dk = 0, e2 = e;
+        switch (e) {
+        case 0: dk = kg > 0 ? -1 : 0; dj = j > 0 ? -1 : 0; e2 = dk ? (dj ? 6 : 4) : (dj ? 2 : 0); break;
+        case 1: dk = -1; e2 = 5; break;
+        case 2: dk = -1; e2 = 6; break;
+        case 3: dk = kg > 0 ? -1 : 0; di = i > 0 ? -1 : 0; e2 = dk ? (di ? 5 : 7) : (di ? 1 : 3); break;
+        case 4: dj = -1; e2 = 6; break;
+        case 7: di = -1; e2 = 5; break;
+        case 8: if (j > 0) { dj = -1; if (i > 0) { di = -1; e2 = 10; } else e2 = 11; } else { di = -1; e2 = 9; } break;
+        case 9: dj = -1; e2 = 10; break;
+        case 11: di = -1; e2 = 10; break;
+        }
+        const int oi = i + di, oj = j + dj, okl = kl + dk;
+        const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl) : -1;
+        if (orr < 0) { atomicExch(p.error_flag, 1); vid[e] = 0; continue; }
+        const McRecord orec = p.recs[orr];
+        const int rk = mc_rank_in_row(d_lut + MC_LEAF_OFF(orec.info), 3 * (int)MC_LEAF_NT(orec.info), mc_owned_mask(oi, oj, kg + dk), e2);
+        if (rk < 0) { atomicExch(p.error_flag, 2); vid[e] = 0; continue; }
+        vid[e] = (long long)(orec.vbase + (unsigned)rk);
+    }
+    // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
+    {
+        int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
+        const long long shift = p.vglobal0 - (long long)p.vlocal0;
+        for (int k = 0; k < nent; k++) out[k] = (int)(vid[row[k]] + shift);
+    }
+    // ---- vertices this cell creates, in creation order
+    unsigned seen = 0;
+    int created = 0;
+    for (int k = 0; k < nent; k++) {
+        const int e = row[k];
+        const unsigned bit = 1u << e;
+        if (!(owned & bit) || (seen & bit)) continue;
+        seen |= bit;
+        const long long slot = (long long)(rec.vbase - p.vlocal0) + created;
+        created++;
+        McF3 pos, col, nsum = {0.f, 0.f, 0.f};
+        const double stp = (double)g.step;
+        const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;       // Cell.x/y/z are voxel coordinates
+        if (e == 12) {
+            // Cell.CalculateCenterVertex (Cell.cs:501-549)
+            double w[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) w[q] = 1.0 / (MC_EPS + fabs(v[q]));
+            double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+            const double ox[8] = {0, 1, 1, 0, 0, 1, 1, 0}, oy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, oz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma unroll
+            for (int q = 0; q < 8; q++) { fx += ox[q] * w[q]; fy += oy[q] * w[q]; fz += oz[q] * w[q]; ff += w[q]; }
+            McF3 fc = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int cdx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, cdy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, cdz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+                const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx[q], cdy[q], cdz[q]) * 3;
+                const float wq = (float)w[q];
+                const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
+                if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
+                else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
+            }
+            pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
+            col.x = (float)(fc.x / ff); col.y = (float)(fc.y / ff); col.z = (float)(fc.z / ff);
+            double g12[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                double s = w[0] * mc_vg(v, 0, a);
+#pragma unroll
+                for (int q = 1; q < 8; q++) s = s + w[q] * mc_vg(v, q, a);
+                g12[a] = s;
+            }
+            int times = 0;
+            for (int q = 0; q < nent; q++) times += (row[q] == 12);
+            const float gx = (float)g12[0], gy = (float)g12[1], gz = (float)g12[2];
+            for (int t = 0; t < times; t++) { nsum.x = nsum.x + gx; nsum.y = nsum.y + gy; nsum.z = nsum.z + gz; }
+        } else {
+            // Cell.AddFaceFromEdgeIndex, new-vertex branch (Cell.cs:313-357)
+            const int dx1 = d_lut[MCL_edgesrelx + e * 2], dx2 = d_lut[MCL_edgesrelx + e * 2 + 1];
+            const int dy1 = d_lut[MCL_edgesrely + e * 2], dy2 = d_lut[MCL_edgesrely + e * 2 + 1];
+            const int dz1 = d_lut[MCL_edgesrelz + e * 2], dz2 = d_lut[MCL_edgesrelz + e * 2 + 1];
+            const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+            const double w1 = 1.0 / (MC_EPS + fabs(v[ro[dz1 * 4 + dy1 * 2 + dx1]]));
+            const double w2 = 1.0 / (MC_EPS + fabs(v[ro[dz2 * 4 + dy2 * 2 + dx2]]));
+            double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+            fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
+            fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
+            const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
+            const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
+            const float f1 = (float)w1, f2 = (float)w2;
+            const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
+            pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
+            col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
+            // gather the gradient contributions of every sharing cell in visiting order (normals[] accumulation
+            // order of the reference); the grid edge starts at lattice point (X, Y, Z) and runs along `axis`
+            const int X = i + min(dx1, dx2), Y = j + min(dy1, dy2), Z = kg + min(dz1, dz2);
+            const int axis = (dx1 != dx2) ? 0 : ((dy1 != dy2) ? 1 : 2);
+            // sharing cells (di, dj, dk relative to (X,Y,Z)) and the edge's local id there, in (k, j, i) order
+            const signed char share[3][4][4] = {
+                {{0, -1, -1, 6}, {0, 0, -1, 4}, {0, -1, 0, 2}, {0, 0, 0, 0}},
+                {{-1, 0, -1, 5}, {0, 0, -1, 7}, {-1, 0, 0, 1}, {0, 0, 0, 3}},
+                {{-1, -1, 0, 10}, {0, -1, 0, 11}, {-1, 0, 0, 9}, {0, 0, 0, 8}}};
+            for (int s = 0; s < 4; s++) {
+                const int ci = X + share[axis][s][0], cj = Y + share[axis][s][1], ck = Z + share[axis][s][2];
+                const int es = share[axis][s][3];
+                if (ci < 0 || cj < 0 || ck < 0 || ci >= g.ncx || cj >= g.ncy || ck >= g.ncz) continue;
+                const int ckl = ck - g.k0;
+                if (ckl < 0 || ckl >= g.nk) { atomicExch(p.error_flag, 3); continue; }
+                const signed char* srow;
+                int snent;
+                double sv[8];
+                if (ci == i && cj == j && ck == kg) {
+                    srow = row; snent = nent;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sv[q] = v[q];
+                } else {
+                    const int sr = mc_find_record(p, ci, cj, ckl);
+                    if (sr < 0) { atomicExch(p.error_flag, 4); continue; }
+                    const unsigned sinfo = p.recs[sr].info;
+                    srow = d_lut + MC_LEAF_OFF(sinfo);
+                    snent = 3 * (int)MC_LEAF_NT(sinfo);
+                    mc_load_cell(g, p.dist, ci, cj, ck, sv);
+                }
+                int times = 0;
+                for (int q = 0; q < snent; q++) times += (srow[q] == es);
+                if (times) mc_add_edge_gradients(sv, es, times, nsum);
+            }
+        }
+        mc_store_vertex(p, slot, pos, col, nsum);
+    }
+}
+
+cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
+{
+    const unsigned n = p.rec_end - p.rec_begin;
+    if (n == 0) return cudaSuccess;
+    mc_emit_kernel<<<(n + 127u) / 128u, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}

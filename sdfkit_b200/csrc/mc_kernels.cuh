@@ -1,0 +1,70 @@
+// mc_kernels.cuh -- shared declarations of the marching-cubes stage (host + device).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// Geometry of one meshing job (a whole grid, or one z-slab of it).  Voxel layout: x fastest,
+// dist[(zl*ny + y)*nx + x], rgb[...*3]; zl = z - z0 (DESIGN.md "data layout").
+struct McGrid {
+    int nx, ny;            // voxel dims in x, y (never partitioned)
+    int nzl;               // slices held locally
+    int z0;                // global z of local slice 0
+    int nz;                // global slice count
+    int step;              // MarchingCubes step (MarchingCubes.cs:49-68)
+    int ncx, ncy, ncz;     // GLOBAL cell counts per axis: cells at x = i*step, i < ncx
+    int k0;                // first GLOBAL cell layer classified locally
+    int nk;                // number of cell layers classified locally (incl. ghost layers)
+    int kown0, kown1;      // GLOBAL cell layers [kown0, kown1) this slab emits
+    int cpr;               // 128-cell chunks per cell row = ceil(ncx/128)
+    float iso;
+    unsigned nchunks;      // nk * ncy * cpr
+};
+
+// One record per active cell, in the reference's visiting order (z outer, y, x inner).
+struct __align__(16) McRecord {
+    unsigned cell;         // local linear cell id: i + ncx*(j + ncy*(k - k0))
+    unsigned info;         // leaf: row offset in the LUT blob [0:14) | ntris [14:18) | uses centre vertex [18]
+    unsigned vbase;        // exclusive prefix of created vertices (slab-local)
+    unsigned tbase;        // exclusive prefix of triangles (slab-local)
+};
+
+// per-chunk packed counts: nactive [0:8) | nverts [8:19) | ntris [19:30)
+#define MC_CNT_ACT(c) ((c) & 0xFFu)
+#define MC_CNT_V(c) (((c) >> 8) & 0x7FFu)
+#define MC_CNT_T(c) (((c) >> 19) & 0x7FFu)
+#define MC_CNT_PACK(a, v, t) ((unsigned)(a) | ((unsigned)(v) << 8) | ((unsigned)(t) << 19))
+
+struct McTotals {          // written by the scan
+    unsigned long long nact, nverts, ntris;
+};
+
+struct McEmitParams {
+    McGrid g;
+    const float* dist;
+    const float* rgb;
+    const unsigned* counts;        // per chunk packed counts
+    const uint4* base;             // per chunk exclusive prefix: x = records, y = verts, z = tris
+    const McRecord* recs;
+    unsigned rec_begin, rec_end;   // records emitted by this slab (owned layers)
+    unsigned vlocal0, tlocal0;     // slab-local prefix at the first owned layer
+    long long vglobal0, tglobal0;  // global ids of the slab's first owned vertex / triangle
+    float* verts;                  // outputs, indexed by (id - vglobal0) / (tri - tglobal0)
+    float* cols;
+    float* nrms;
+    int* tris;
+    unsigned* aabb_keys;           // 6 ordered-uint keys: min xyz, max xyz
+    int has_xf;
+    float M[16];                   // Mesh.Transform matrix (row-major, row-vector convention)
+    float N[16];                   // its normal transform
+    int* error_flag;
+};
+
+// host-side launchers (mc_kernels.cu)
+cudaError_t mc_init_tables();
+cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s);
+cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
+                           McTotals* totals, cudaStream_t s);
+size_t mc_scan_workspace_bytes(unsigned nchunks);
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+                              McRecord* recs, cudaStream_t s);
+cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);

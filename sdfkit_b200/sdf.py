@@ -1,0 +1,99 @@
+"""The `Sdf` delegate as a GPU object, and the SdfEx facade (ToVoxels / ToMesh / ToImage).
+
+Reference: SdfKit/Sdf.cs:6-99.  `SdfExpr.ToSdf()` returns a GpuSdf: its expression tree has been lowered
+to CUDA C++ and NVRTC-compiled for sm_100a.  It is still callable like the delegate
+(`sdf(points, colorsAndDistances)`, Sdf.cs:8) -- that call runs the JIT-compiled kernel on the batch.
+Opaque callables (the reference's hand-written batch lambdas, Sdfs.*, SdfFuncs.*) are rejected by every
+consumer with NotSupportedError: no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import numerics
+from .exprs import SdfExpr, lower
+
+
+class SdfConfig:
+    DefaultBatchSize = 2 * 1024        # Sdf.cs:13 (a tuning hint with no effect on results; ignored on the GPU)
+
+
+def require_gpu_sdf(sdf):
+    if isinstance(sdf, GpuSdf):
+        return sdf
+    if isinstance(sdf, SdfExpr):
+        return sdf.ToSdf()
+    raise N.NotSupportedError(
+        "only SDFs built from SdfExprs (SdfExpr.ToSdf()) run on the GPU path; opaque callables such as %r are "
+        "rejected rather than run on a CPU fallback" % (sdf,))
+
+
+class GpuSdf:
+    """Sdf delegate backed by sdfk_sdf (JIT-compiled sample / eval / render kernels)."""
+
+    def __init__(self, expr, ctx=None):
+        self.ctx = ctx or N.Context.default()
+        self.lowered = lower(expr)
+        body = self.lowered.body.encode()
+        h = C.c_void_p()
+        N.check(N.lib().sdfk_sdf_compile(self.ctx.handle, body, len(body), C.byref(h)))
+        self.handle = h
+
+    # ---- the delegate: void Sdf(Memory<Vector3> points, Memory<Vector4> colorsAndDistances)
+    def __call__(self, points, colorsAndDistances=None):
+        pts = N.f32c(points).reshape(-1, 3)
+        out = colorsAndDistances
+        if out is None:
+            out = np.empty((pts.shape[0], 4), dtype=np.float32)
+        if out.dtype != np.float32 or not out.flags.c_contiguous or out.size != pts.shape[0] * 4:
+            raise ValueError("colorsAndDistances must be a contiguous float32 array of points.Length Vector4s")
+        N.check(N.lib().sdfk_sdf_eval(self.handle, N.fptr(pts), N.fptr(out), pts.shape[0]))
+        return out
+
+    # ---- SdfEx (Sdf.cs:20-99)
+    def Sample(self, points, distances, batchSize=SdfConfig.DefaultBatchSize, maxDegreeOfParallelism=-1):
+        return self(points, distances)
+
+    def ToVoxels(self, min, max, nx, ny, nz, batchSize=SdfConfig.DefaultBatchSize, maxDegreeOfParallelism=-1,
+                 clipToBounds=True):
+        from .voxels import Voxels
+        return Voxels._sample(self, min, max, nx, ny, nz, clip=clipToBounds)
+
+    def ToMesh(self, min, max, nx, ny, nz, batchSize=SdfConfig.DefaultBatchSize, maxDegreeOfParallelism=-1,
+               clipToBounds=True, isoValue=0.0, step=1, progress=None):
+        voxels = self.ToVoxels(min, max, nx, ny, nz, batchSize, maxDegreeOfParallelism, clipToBounds)
+        try:
+            return voxels.ToMesh(isoValue, step, progress)
+        finally:
+            voxels.Dispose()
+
+    def ToImage(self, width, height, *camera, verticalFieldOfViewDegrees=60.0, nearPlaneDistance=1.0,
+                farPlaneDistance=100.0, depthIterations=40, batchSize=SdfConfig.DefaultBatchSize,
+                maxDegreeOfParallelism=-1):
+        """ToImage(w, h, viewTransform) or ToImage(w, h, cameraPosition, cameraTarget, cameraUpVector)."""
+        from .raymarcher import RayMarcher
+        if len(camera) == 1:
+            view = np.asarray(camera[0], dtype=np.float32).reshape(4, 4)
+        elif len(camera) == 3:
+            view = numerics.create_look_at(*camera)          # Sdf.cs:95
+        else:
+            raise TypeError("ToImage takes a view matrix or (position, target, up)")
+        rm = RayMarcher(width, height, self, batchSize, maxDegreeOfParallelism)
+        rm.ViewTransform = view
+        rm.VerticalFieldOfViewDegrees = verticalFieldOfViewDegrees
+        rm.NearPlaneDistance = nearPlaneDistance
+        rm.FarPlaneDistance = farPlaneDistance
+        rm.DepthIterations = depthIterations
+        return rm.Render()
+
+    def Dispose(self):
+        if self.handle:
+            N.lib().sdfk_sdf_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass

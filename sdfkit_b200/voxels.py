@@ -1,0 +1,252 @@
+"""Voxels, MarchingCubes and Mesh -- the host-side mirror of SdfKit/Voxels.cs, MarchingCubes.cs, Mesh.cs.
+
+The voxel field lives in HBM behind an sdfk_voxels handle (device layout x-fastest); the reference's public
+arrays `Values[x,y,z]` / `Colors[x,y,z]` are materialised lazily, in the C# layout, on first access.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import numerics
+
+
+class Mesh:
+    """SdfKit.Mesh (Mesh.cs): Vertices / Colors / Normals (n x 3 float32), Triangles (flat int32, 3 per triangle)."""
+
+    def __init__(self, vertices, colors, normals, triangles, vmin, vmax):
+        self.Vertices, self.Colors, self.Normals, self.Triangles = vertices, colors, normals, triangles
+        self.Min, self.Max = vmin, vmax
+
+    @property
+    def Center(self):
+        return ((self.Min + self.Max).astype(np.float32) * np.float32(0.5)).astype(np.float32)
+
+    @property
+    def Size(self):
+        return (self.Max - self.Min).astype(np.float32)
+
+    @property
+    def Radius(self):
+        return numerics.length3(self.Size) * np.float32(0.5)
+
+    def WriteObj(self, path_or_file):
+        """Mesh.WriteObj (Mesh.cs:66-97): "v x y z", "vn x y z", "f i//i j//j k//k" (1-based)."""
+        fmt = _net_float
+        close = False
+        w = path_or_file
+        if isinstance(path_or_file, str):
+            w = open(path_or_file, "w", newline="\n")
+            close = True
+        try:
+            for v in self.Vertices:
+                w.write("v %s %s %s\n" % (fmt(v[0]), fmt(v[1]), fmt(v[2])))
+            for v in self.Normals:
+                w.write("vn %s %s %s\n" % (fmt(v[0]), fmt(v[1]), fmt(v[2])))
+            t = np.asarray(self.Triangles).reshape(-1, 3) + 1
+            for a, b, c in t:
+                w.write("f %d//%d %d//%d %d//%d\n" % (a, a, b, b, c, c))
+        finally:
+            if close:
+                w.close()
+
+
+def _net_float(x):
+    """Shortest round-trippable float32 text, as .NET Core 3.0+ `float.ToString()` prints (invariant culture)."""
+    x = np.float32(x)
+    if np.isnan(x):
+        return "NaN"
+    if np.isinf(x):
+        return "Infinity" if x > 0 else "-Infinity"
+    s = np.format_float_positional(x, unique=True, trim="-")
+    if x != 0 and (abs(float(x)) >= 1e15 or abs(float(x)) < 1e-5):
+        s = np.format_float_scientific(x, unique=True, trim="-", exp_digits=2).replace("e", "E")
+    return "-0" if (s == "0" and np.signbit(x)) else s
+
+
+class GpuMesh:
+    """Handle-level view of an sdfk_mesh (used by the multi-GPU driver and the benchmark)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def counts(self):
+        nv, nt = C.c_int64(), C.c_int64()
+        N.check(N.lib().sdfk_mesh_counts(self.handle, C.byref(nv), C.byref(nt)))
+        return nv.value, nt.value
+
+    def stats(self):
+        s = (C.c_double * 8)()
+        N.check(N.lib().sdfk_mesh_stats(self.handle, s))
+        return {"classify_ms": s[0], "scan_ms": s[1], "compact_ms": s[2], "emit_ms": s[3],
+                "active_cells": int(s[4]), "records": int(s[5]), "chunks": int(s[6])}
+
+    def download(self):
+        nv, nt = self.counts()
+        v = np.empty((nv, 3), dtype=np.float32)
+        c = np.empty((nv, 3), dtype=np.float32)
+        n = np.empty((nv, 3), dtype=np.float32)
+        t = np.empty(nt * 3, dtype=np.int32)
+        aabb = np.zeros(6, dtype=np.float32)
+        N.check(N.lib().sdfk_mesh_export(self.handle, N.fptr(v), N.fptr(c), N.fptr(n),
+                                         t.ctypes.data_as(C.POINTER(C.c_int32)), N.fptr(aabb)))
+        return Mesh(v, c, n, t, aabb[:3].copy(), aabb[3:].copy())
+
+    def destroy(self):
+        if self.handle:
+            N.lib().sdfk_mesh_destroy(self.handle)
+            self.handle = None
+
+    __del__ = destroy
+
+
+class Voxels:
+    """SdfKit.Voxels (Voxels.cs).  Construct with Voxels(values, colors, min, max) from host arrays in the C#
+    layout, Voxels(min, max, nx, ny, nz) for an empty grid, or Voxels.SampleSdf(sdf, min, max, nx, ny, nz)."""
+
+    def __init__(self, *args, ctx=None):
+        self.ctx = ctx or N.Context.default()
+        self.handle = None
+        self._values = self._colors = None
+        if len(args) == 4:                                   # Voxels(float[,,] values, Vector3[,,] colors, min, max)
+            values, colors, vmin, vmax = args
+            values = N.f32c(values)
+            if values.ndim != 3:
+                raise ValueError("values must be float[nx, ny, nz]")
+            nx, ny, nz = values.shape
+            colors = None if colors is None else N.f32c(colors).reshape(nx, ny, nz, 3)
+            self._set_grid(vmin, vmax, nx, ny, nz)
+            h = C.c_void_p()
+            N.check(N.lib().sdfk_voxels_import(self.ctx.handle, N.fptr(values), N.fptr(colors), N.fptr(self.Min),
+                                               N.fptr(self.Max), nx, ny, nz, C.byref(h)))
+            self.handle = h
+        elif len(args) == 5:                                 # Voxels(min, max, nx, ny, nz): zero-filled
+            vmin, vmax, nx, ny, nz = args
+            self._set_grid(vmin, vmax, nx, ny, nz)
+        else:
+            raise TypeError("Voxels(values, colors, min, max) or Voxels(min, max, nx, ny, nz)")
+
+    def _set_grid(self, vmin, vmax, nx, ny, nz):
+        self.Min, self.Max = numerics.vec3(vmin), numerics.vec3(vmax)
+        self.NX, self.NY, self.NZ = int(nx), int(ny), int(nz)
+        f = np.float32
+        self.DX = (self.Max[0] - self.Min[0]) / f(nx) if nx >= 1 else f(0)     # Voxels.cs:32-34
+        self.DY = (self.Max[1] - self.Min[1]) / f(ny) if ny >= 1 else f(0)
+        self.DZ = (self.Max[2] - self.Min[2]) / f(nz) if nz >= 1 else f(0)
+
+    # ---- IBoundedVolume
+    @property
+    def Center(self):
+        return ((self.Min + self.Max).astype(np.float32) * np.float32(0.5)).astype(np.float32)
+
+    @property
+    def Size(self):
+        return (self.Max - self.Min).astype(np.float32)
+
+    @property
+    def Radius(self):
+        return numerics.length3(self.Size) * np.float32(0.5)
+
+    # ---- sampling
+    @classmethod
+    def _sample(cls, sdf, vmin, vmax, nx, ny, nz, clip):
+        from .sdf import require_gpu_sdf
+        sdf = require_gpu_sdf(sdf)
+        v = cls(vmin, vmax, nx, ny, nz, ctx=sdf.ctx)
+        h = C.c_void_p()
+        N.check(N.lib().sdfk_voxels_sample(sdf.ctx.handle, sdf.handle, N.fptr(v.Min), N.fptr(v.Max), v.NX, v.NY, v.NZ,
+                                           1 if clip else 0, C.byref(h)))
+        v.handle = h
+        return v
+
+    @classmethod
+    def SampleSdf(cls, sdf, min, max, nx, ny, nz, batchSize=2048, maxDegreeOfParallelism=-1):
+        """Voxels.SampleSdf (static, Voxels.cs:169-174).  batchSize / maxDegreeOfParallelism: accepted, no effect."""
+        return cls._sample(sdf, min, max, nx, ny, nz, clip=False)
+
+    def Resample(self, sdf, clip=False):
+        """Instance Voxels.SampleSdf (Voxels.cs:72-125): re-fill this grid in place."""
+        from .sdf import require_gpu_sdf
+        sdf = require_gpu_sdf(sdf)
+        if self.handle is None:
+            other = Voxels._sample(sdf, self.Min, self.Max, self.NX, self.NY, self.NZ, clip)
+            self.handle, other.handle = other.handle, None
+        else:
+            N.check(N.lib().sdfk_voxels_resample(self.handle, sdf.handle, 1 if clip else 0))
+        self._values = self._colors = None
+
+    def ClipToBounds(self):
+        self._ensure()
+        N.check(N.lib().sdfk_voxels_clip(self.handle))
+        self._values = None
+
+    def _ensure(self):
+        if self.handle is None:   # an empty Voxels(min,max,n..): zeros
+            z = np.zeros((self.NX, self.NY, self.NZ), dtype=np.float32)
+            h = C.c_void_p()
+            N.check(N.lib().sdfk_voxels_import(self.ctx.handle, N.fptr(z), None, N.fptr(self.Min), N.fptr(self.Max),
+                                               self.NX, self.NY, self.NZ, C.byref(h)))
+            self.handle = h
+
+    # ---- host materialisation (C# layout)
+    @property
+    def Values(self):
+        if self._values is None:
+            self._ensure()
+            out = np.empty((self.NX, self.NY, self.NZ), dtype=np.float32)
+            N.check(N.lib().sdfk_voxels_export(self.handle, N.fptr(out), None))
+            self._values = out
+        return self._values
+
+    @property
+    def Colors(self):
+        if self._colors is None:
+            self._ensure()
+            out = np.empty((self.NX, self.NY, self.NZ, 3), dtype=np.float32)
+            N.check(N.lib().sdfk_voxels_export(self.handle, None, N.fptr(out)))
+            self._colors = out
+        return self._colors
+
+    def __getitem__(self, idx):
+        ix, iy, iz = idx
+        return self.Values[ix, iy, iz]
+
+    # ---- meshing
+    def ToMesh(self, isoValue=0.0, step=1, progress=None):
+        return MarchingCubes.CreateMesh(self, isoValue, step, progress)
+
+    def Dispose(self):
+        if self.handle:
+            N.lib().sdfk_voxels_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass
+
+
+class MarchingCubes:
+    """SdfKit.MarchingCubes (MarchingCubes.cs:39-92)."""
+
+    @staticmethod
+    def CreateGpuMesh(volume, isoValue=0.0, step=1, progress=None, transform=True):
+        volume._ensure()
+        M = Nm = None
+        if transform:
+            M, Nm = numerics.mesh_transforms(volume.Min, volume.Max, volume.NX, volume.NY, volume.NZ)
+            M, Nm = N.f32c(M), N.f32c(Nm)
+        cb = N.PROGRESS_FN((lambda f, _u: progress(f)) if progress else (lambda f, _u: None))
+        h = C.c_void_p()
+        N.check(N.lib().sdfk_mesh_create(volume.ctx.handle, volume.handle, float(isoValue), int(step), N.fptr(M), N.fptr(Nm),
+                                         cb if progress else C.cast(None, N.PROGRESS_FN), None, C.byref(h)))
+        return GpuMesh(h)
+
+    @staticmethod
+    def CreateMesh(volume, isoValue=0.0, step=1, progress=None):
+        gm = MarchingCubes.CreateGpuMesh(volume, isoValue, step, progress)
+        try:
+            return gm.download()
+        finally:
+            gm.destroy()

@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path (through the C ABI / host mirror) against the CPU oracle on the same
+inputs.  Bar (BASELINE.json north star): bit-exact cube indices, triangle counts and index buffers;
+distances, colours and vertex positions within 1e-5 relative -- in practice these tests assert
+bit-exact equality everywhere, because both sides perform the same IEEE operations (no FMA)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def sk():
+    import sdfkit_b200
+    return sdfkit_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bits_equal(a, b, what):
+    a, b = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+    assert a.shape == b.shape, what
+    same = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+    if not same.all():
+        bad = np.argwhere(~same)
+        i = tuple(bad[0])
+        raise AssertionError("%s: %d of %d values differ; first at %s: gpu=%r oracle=%r (max rel err %.3g)" % (
+            what, len(bad), a.size, i, a[i], b[i], float(np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))))
+
+
+def scenes_list(sk):
+    from sdfkit_b200 import scenes
+    return {"sphere": scenes.sphere(), "readme": scenes.readme_scene(), "perf": scenes.perf_scene(), "csg50": scenes.csg50()}
+
+
+# ---------------------------------------------------------------------------------------------- sampling
+
+@pytest.mark.parametrize("name,dims,clip", [
+    ("sphere", (64, 64, 64), True),          # BASELINE config 1
+    ("readme", (64, 64, 64), True),          # config 2 scene at test scale
+    ("readme", (128, 128, 128), False),
+    ("perf", (50, 37, 29), True),            # ragged: nx % 4 != 0 -> scalar store path
+    ("csg50", (96, 96, 48), True),           # config 3 scene
+    ("sphere", (1, 1, 1), False),            # Tests/VolumeTests.cs:39-58
+    ("sphere", (5, 7, 11), True),
+    ("readme", (260, 4, 3), True),           # partial last 128-voxel tile on the vector path
+])
+def test_sample_matches_oracle(sk, oracle, name, dims, clip):
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    vox = sdf.ToVoxels(mn, mx, nx, ny, nz, clipToBounds=clip)
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, clip_to_bounds=clip, threads=4)
+    assert_bits_equal(vox.Values, ov, "%s %s distances" % (name, dims))
+    assert_bits_equal(vox.Colors, oc, "%s %s colours" % (name, dims))
+
+
+def test_sample_reference_test_values(sk):
+    # Tests/VolumeTests.cs:82-106,134 and Tests/SdfTests.cs:12-26 through the GPU path
+    sdf = sk.SdfExprs.Sphere(0.5).ToSdf()
+    v5 = sk.Voxels.SampleSdf(sdf, (-1, -1, -1), (1, 1, 1), 5, 5, 5)
+    assert abs(v5[2, 2, 2] + 0.5) < 1e-3
+    v128 = sdf.ToVoxels((-1, -1, -1), (1, 1, 1), 128, 128, 128)
+    assert abs(v128[63, 63, 63] + 0.5) < 2e-2
+    assert (v128.NX, v128.NY, v128.NZ) == (128, 128, 128)
+    assert abs(v128.Size[0] - 2.0) < 1e-6
+
+
+def test_sdf_delegate_matches_oracle(sk, oracle):
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-4, 4, (10007, 3)).astype(np.float32)
+    for name, (expr, _, _) in scenes_list(sk).items():
+        sdf = expr.ToSdf()
+        out = np.zeros((len(pts), 4), dtype=np.float32)
+        sdf(pts, out)
+        assert_bits_equal(out, oracle.eval_sdf(sdf.lowered, pts), name + " delegate")
+    assert sdf(np.zeros((0, 3), dtype=np.float32)).shape == (0, 4)
+
+
+def test_opaque_sdf_is_rejected(sk):
+    opaque = lambda pts, out: None     # the reference would run this on the CPU
+    with pytest.raises(sk.NotSupportedError):
+        sk.Voxels.SampleSdf(opaque, (-1, -1, -1), (1, 1, 1), 8, 8, 8)
+    with pytest.raises(sk.NotSupportedError):
+        sk.RayMarcher(8, 8, opaque)
+
+
+def test_voxels_import_export_roundtrip(sk):
+    rng = np.random.default_rng(5)
+    vals = rng.uniform(-1, 1, (37, 21, 45)).astype(np.float32)
+    cols = rng.uniform(0, 1, (37, 21, 45, 3)).astype(np.float32)
+    v = sk.Voxels(vals, cols, (-1, -1, -1), (1, 1, 1))
+    assert_bits_equal(v.Values, vals, "values roundtrip")
+    assert_bits_equal(v.Colors, cols, "colours roundtrip")
+    v.ClipToBounds()
+    exp = vals.copy()
+    for sl in [np.s_[0], np.s_[-1], np.s_[:, 0], np.s_[:, -1], np.s_[:, :, 0], np.s_[:, :, -1]]:
+        exp[sl] = f32(2.0) / f32(37)
+    assert_bits_equal(v.Values, exp, "ClipToBounds")
+
+
+# ---------------------------------------------------------------------------------------------- marching cubes
+
+def mesh_pair(sk, oracle, values, colors, mn, mx, iso=0.0, step=1):
+    vox = sk.Voxels(values, colors, mn, mx)
+    gm = sk.MarchingCubes.CreateGpuMesh(vox, iso, step)
+    mesh = gm.download()
+    om = oracle.marching_cubes(values, colors, np.float32(mn), np.float32(mx), iso=iso, step=step)
+    return mesh, om, gm
+
+
+def assert_mesh_equal(mesh, om, what):
+    assert len(mesh.Vertices) == len(om.vertices), "%s: vertex count %d vs %d" % (what, len(mesh.Vertices), len(om.vertices))
+    assert len(mesh.Triangles) == om.triangles.size, "%s: triangle count" % what
+    assert np.array_equal(mesh.Triangles.reshape(-1, 3), om.triangles), what + ": triangle indices / order"
+    assert_bits_equal(mesh.Vertices, om.vertices, what + " vertex positions")
+    assert_bits_equal(mesh.Colors, om.colors, what + " vertex colours")
+    assert_bits_equal(mesh.Normals, om.normals, what + " normals")
+    if len(om.vertices):
+        assert_bits_equal(mesh.Min, om.min, what + " aabb min")
+        assert_bits_equal(mesh.Max, om.max, what + " aabb max")
+
+
+@pytest.mark.parametrize("name,dims,clip", [
+    ("sphere", (64, 64, 64), True),          # config 1: 4,874 active cells, 4,872 vertices, 9,740 triangles
+    ("readme", (64, 64, 64), True),
+    ("readme", (128, 128, 128), True),
+    ("perf", (50, 37, 29), True),
+    ("csg50", (96, 96, 48), True),
+    ("sphere", (131, 9, 6), True),           # two 128-cell chunks per row, ragged
+])
+def test_mesh_matches_oracle(sk, oracle, name, dims, clip):
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    vox = sdf.ToVoxels(mn, mx, nx, ny, nz, clipToBounds=clip)
+    mesh = vox.ToMesh()
+    om = oracle.marching_cubes(vox.Values, vox.Colors, np.float32(mn), np.float32(mx))
+    assert_mesh_equal(mesh, om, "%s %s" % (name, dims))
+    if name == "sphere" and dims == (64, 64, 64):
+        assert (len(om.vertices), len(om.triangles), om.active_cells) == (4872, 9740, 4874)
+    assert len(om.vertices) > 0
+
+
+def test_reference_goldens_through_gpu(sk, oracle):
+    """The reference's vertex-count goldens, meshed by the GPU path."""
+    from oracle import sdf_numpy as S
+    E = sk.SdfExprs
+    # Tests/SdfTests.cs:42-52 (the one SdfExpr -> ToSdf -> ToMesh test) and :28-39
+    assert len(E.Solid(lambda p: p.Length() - 0.5).ToSdf().ToMesh((-1, -1, -1), (1, 1, 1), 32, 32, 32).Vertices) == 1248
+    assert len(E.Sphere(0.5).ToSdf().ToMesh((-1, -1, -1), (1, 1, 1), 32, 32, 32).Vertices) == 1248
+    # Tests/MarchingCubesTests.cs: Sphere5 54, Sphere10 312, Unclipped 0, Clipped 384, Box10 384, Cylinder50 7456, Sphere128 72240
+    def count(expr, mn, mx, n, clip):
+        v = sk.Voxels.SampleSdf(expr.ToSdf(), mn, mx, n, n, n)
+        if clip:
+            v.ClipToBounds()
+        return v.ToMesh()
+    m = count(E.Sphere(1.0), (-1.5,) * 3, (1.5,) * 3, 5, False)
+    assert len(m.Vertices) == 54 and np.linalg.norm(m.Center) < 1e-6 and abs(m.Size[0] / 2 - 1) < 0.3
+    m = count(E.Sphere(2.0), (-2.5,) * 3, (2.5,) * 3, 10, False)
+    assert len(m.Vertices) == 312 and np.linalg.norm(m.Center) < 1e-6
+    m = count(E.Sphere(2.0), (-1,) * 3, (1,) * 3, 10, False)
+    assert len(m.Vertices) == 0 and len(m.Triangles) == 0
+    m = count(E.Sphere(2.0), (-1,) * 3, (1,) * 3, 10, True)
+    assert len(m.Vertices) == 384 and abs(m.Size[0] - 2.0) < 1e-1
+    m = count(E.Box(2.0), (-2.5,) * 3, (2.5,) * 3, 10, False)
+    assert len(m.Vertices) == 384
+    seen = []
+    v = sk.Voxels.SampleSdf(E.Cylinder(1, 3).ToSdf(), (-1.5, -3.5, -1.5), (1.5, 3.5, 1.5), 50, 50, 50)
+    assert len(v.ToMesh().Vertices) == 7456
+    v = sk.Voxels.SampleSdf(E.Sphere(3.0).ToSdf(), (f32(-3.1),) * 3, (f32(3.1),) * 3, 128, 128, 128)
+    m = v.ToMesh(progress=seen.append)
+    assert len(m.Vertices) == 72240
+    assert min(seen) < 1e-6 and max(seen) > 1 - 1e-6 and all(0 <= f <= 1 for f in seen)
+    assert abs(m.Size[0] / 2 - 3.0) < 0.1
+    # ColoredSpheres (opaque SdfFuncs in the reference): oracle-sampled voxels imported, meshed on the GPU
+    fn = S.union(S.translate(S.with_color(S.sphere(f32(0.4)), (1.0, 0.2, 0.3)), (-1, 0, 0)),
+                 S.translate(S.with_color(S.sphere(f32(0.2)), (0.1, 1.0, 0.3)), (1, 0, 0)))
+    vals, cols = oracle.sample(oracle.numpy_sdf(fn), np.float32([-3] * 3), np.float32([3] * 3), 32, 32, 32)
+    m = sk.Voxels(vals, cols, (-3,) * 3, (3,) * 3).ToMesh()
+    assert len(m.Vertices) == 104 and m.Colors[0][0] > 0.5
+
+
+@pytest.mark.parametrize("n,seed", [(24, 0), (64, 0), (33, 7)])
+def test_white_noise_all_lewiner_cases(sk, oracle, n, seed):
+    """Coverage input of SURVEY.md 8d: white noise reaches every ambiguous Lewiner branch (cases 3,4,6,7,10,12,13,
+    face/interior tests, centre vertices) -- parity there is pinned only by the oracle restatement."""
+    rng = np.random.default_rng(seed)
+    vals = rng.uniform(-1, 1, (n, n, n)).astype(np.float32)
+    cols = rng.uniform(0, 1, (n, n, n, 3)).astype(np.float32)
+    mesh, om, gm = mesh_pair(sk, oracle, vals, cols, (-1, -1, -1), (1, 1, 1))
+    assert all(om.case_hist[c] > 0 for c in range(1, 15)), om.case_hist
+    assert_mesh_equal(mesh, om, "white noise %d" % n)
+
+
+@pytest.mark.parametrize("dims", [(40, 23, 17), (130, 5, 4), (3, 3, 3), (2, 2, 2), (1, 4, 4), (4, 4, 1)])
+def test_white_noise_ragged_grids(sk, oracle, dims):
+    rng = np.random.default_rng(11)
+    vals = rng.uniform(-1, 1, dims).astype(np.float32)
+    cols = rng.uniform(0, 1, dims + (3,)).astype(np.float32)
+    mesh, om, gm = mesh_pair(sk, oracle, vals, cols, (-1, -2, -3), (1, 2, 3))
+    assert_mesh_equal(mesh, om, "ragged %s" % (dims,))
+
+
+@pytest.mark.parametrize("step,iso", [(2, 0.0), (3, 0.0), (1, 0.25), (2, -0.1)])
+def test_step_and_isovalue(sk, oracle, step, iso):
+    """Public parameters of MarchingCubes.CreateMesh (MarchingCubes.cs:39) the reference's tests never vary."""
+    rng = np.random.default_rng(2)
+    vals = rng.uniform(-1, 1, (36, 31, 29)).astype(np.float32)
+    cols = rng.uniform(0, 1, (36, 31, 29, 3)).astype(np.float32)
+    mesh, om, gm = mesh_pair(sk, oracle, vals, cols, (-1, -1, -1), (1, 1, 1), iso=iso, step=step)
+    assert len(om.vertices) > 0
+    assert_mesh_equal(mesh, om, "step %d iso %g" % (step, iso))
+
+
+def test_cube_index_census_matches(sk, oracle):
+    """Cube indices / per-cell triangle counts: the GPU's totals must equal the oracle's per-cell debug arrays."""
+    expr, mn, mx = scenes_list(sk)["readme"]
+    vox = expr.ToSdf().ToVoxels(mn, mx, 64, 64, 64)
+    gm = sk.MarchingCubes.CreateGpuMesh(vox)
+    om = oracle.marching_cubes(vox.Values, vox.Colors, np.float32(mn), np.float32(mx), debug=True)
+    active = int(((om.cell_index != 0) & (om.cell_index != 255)).sum())
+    assert gm.stats()["active_cells"] == active == om.active_cells == 15218
+    assert gm.counts() == (len(om.vertices), int(om.cell_ntris.sum())) == (15168, 30236)
+
+
+# ---------------------------------------------------------------------------------------------- ray marcher
+
+@pytest.mark.parametrize("name,w,h", [("readme", 192, 108), ("perf", 101, 57), ("csg50", 64, 48), ("sphere", 50, 30)])
+def test_render_matches_oracle(sk, oracle, name, w, h):
+    from sdfkit_b200 import numerics, scenes
+    expr, _, _ = scenes_list(sk)[name]
+    sdf = expr.ToSdf()
+    img = sdf.ToImage(w, h, *scenes.CAMERA)
+    view = numerics.create_look_at(*scenes.CAMERA)
+    ref = oracle.render(sdf.lowered, w, h, view=view, bands=4)
+    assert img.Array.shape == (h, w, 3)
+    assert_bits_equal(img.Array, ref, name + " ToImage")
+    assert np.isfinite(img.Array).all() and img.Array.max() <= 1.1 + 1e-6
+
+
+def test_render_depth_goldens_and_parity(sk, oracle):
+    # Tests/RayMarcherTests.cs:10-75 with SdfExpr equivalents of the opaque Sdfs
+    E = sk.SdfExprs
+    w, h = 50, 30
+    sphere = sk.RayMarcher(w, h, E.Sphere(1.0).ToSdf()).RenderDepth()
+    assert (sphere.Width, sphere.Height) == (w, h)
+    assert abs(sphere[w // 2, h // 2] - 4.0) < 1e-2 and sphere[0, 0] > 9.0
+    box = sk.RayMarcher(w, h, E.Box(1.0).ToSdf()).RenderDepth()
+    assert abs(box[w // 2, h // 2] - 4.0) < 1e-2 and box[0, 0] > 9.0
+    r = f32(0.25)
+    cyl_sdf = E.Cylinder(r, r * 2).RepeatX(4 * r).ToSdf()
+    cyl = sk.RayMarcher(w, h, cyl_sdf).RenderDepth()
+    assert abs(cyl[w // 2, h // 2 - 2] - (5 - r)) < 1e-1 and cyl[0, 0] > 9.0
+    plane = sk.RayMarcher(w, h, E.Solid(lambda p: p.Z).ToSdf()).RenderDepth()       # Sdfs.PlaneXY()
+    assert abs(plane[w // 2, h // 2] - 5.0) < 1e-2 and plane[0, 0] < 9.0
+    assert_bits_equal(cyl.Array, oracle.render_depth(cyl_sdf.lowered, w, h), "cylinder depth")
+
+
+def test_render_row_bands_equal_full_image(sk):
+    from sdfkit_b200 import scenes
+    expr, _, _ = scenes.readme_scene()
+    rm = sk.RayMarcher(160, 90, expr.ToSdf())
+    from sdfkit_b200 import numerics
+    rm.ViewTransform = numerics.create_look_at(*scenes.CAMERA)
+    full = rm.Render().Array
+    parts = [rm.Render(r0, r1).Array for r0, r1 in [(0, 23), (23, 46), (46, 69), (69, 90)]]
+    assert_bits_equal(np.concatenate(parts), full, "row bands")
