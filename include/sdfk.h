@@ -55,6 +55,10 @@ int sdfk_ctx_stream(sdfk_ctx* ctx, void** cuda_stream);
 /* CUDA-event stopwatch on the ctx stream (device time between the two calls) */
 int sdfk_ctx_timer_start(sdfk_ctx* ctx);
 int sdfk_ctx_timer_stop(sdfk_ctx* ctx, float* milliseconds);
+/* event marks on the ctx stream: record mark `slot` (0..63) without synchronising; elapsed = device ms between
+ * two recorded marks (synchronises on the later one) */
+int sdfk_ctx_mark(sdfk_ctx* ctx, int slot);
+int sdfk_ctx_elapsed(sdfk_ctx* ctx, int slot_a, int slot_b, float* milliseconds);
 /* how many kernels this ctx has launched so far */
 int sdfk_ctx_launch_count(sdfk_ctx* ctx, int64_t* launches);
 

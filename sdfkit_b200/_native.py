@@ -24,6 +24,8 @@ SIGNATURES = {
     "sdfk_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sdfk_ctx_timer_start": (C.c_int, [_vp]),
     "sdfk_ctx_timer_stop": (C.c_int, [_vp, _fp]),
+    "sdfk_ctx_mark": (C.c_int, [_vp, C.c_int]),
+    "sdfk_ctx_elapsed": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     "sdfk_ctx_launch_count": (C.c_int, [_vp, _i64p]),
     "sdfk_sdf_compile": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
     "sdfk_sdf_destroy": (C.c_int, [_vp]),
@@ -133,6 +135,14 @@ class Context:
     def timer_stop(self):
         ms = C.c_float()
         check(lib().sdfk_ctx_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def mark(self, slot):
+        check(lib().sdfk_ctx_mark(self.handle, int(slot)))
+
+    def elapsed(self, slot_a, slot_b):
+        ms = C.c_float()
+        check(lib().sdfk_ctx_elapsed(self.handle, int(slot_a), int(slot_b), C.byref(ms)))
         return ms.value
 
     def launch_count(self):

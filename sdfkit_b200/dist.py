@@ -1,0 +1,209 @@
+"""Multi-GPU sharding of the hot path: one process per GPU (torch.distributed for the plumbing).
+
+The grid shards into contiguous z-slabs of CELL LAYERS; a rank samples its own slices plus a halo (one cell
+layer below, one above -- recomputed from the analytic SDF, never exchanged), classifies them, and the only
+data-path collective is the all-gather of per-slab (vertices, triangles) counts that fixes every rank's global
+vertex / triangle offsets (the reference numbers vertices layer-major, so a slab's ids are a contiguous range).
+The mesh gather to rank 0 and the row-band image gather are point-to-point copies.  SURVEY.md section 8e.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import numerics
+from .sdf import require_gpu_sdf
+from .voxels import GpuMesh, Mesh
+
+
+def cells_along(n, step):
+    """Cells visited along one axis (MarchingCubes.cs:49-68): x = 0, step, ... while x < n - step."""
+    return 0 if n <= step else (n - step + step - 1) // step
+
+
+def partition(n, parts):
+    """Contiguous ranges of ceil(n/parts) items, like Vec3Data.PartitionVertically (VectorData.cs:512-526)."""
+    size = (n + parts - 1) // parts if parts > 0 else n
+    out, lo = [], 0
+    for _ in range(parts):
+        hi = min(n, lo + size)
+        out.append((lo, max(lo, hi)))
+        lo = max(lo, hi)
+    return out
+
+
+def slab_slices(kb, ke, step, nz):
+    """Voxel slices [z_begin, z_end) a rank must hold to mesh cell layers [kb, ke): its own planes plus the ghost
+    layer below (owner of the vertices on the shared plane) and above (contributes to their normals)."""
+    ncz = cells_along(nz, step)
+    if ke <= kb:
+        return 0, 1
+    k0 = max(kb - 1, 0)
+    k1 = min(ke + 1, ncz)
+    return k0 * step, k1 * step + 1
+
+
+def exclusive_offsets(counts):
+    """counts: int64[world, 2] (vertices, triangles per rank) -> (int64[world, 2] exclusive prefix, totals[2])."""
+    counts = np.asarray(counts, dtype=np.int64).reshape(-1, 2)
+    excl = np.zeros_like(counts)
+    excl[1:] = np.cumsum(counts, axis=0)[:-1]
+    return excl, counts.sum(axis=0)
+
+
+class SlabMesher:
+    """One rank's share of Sdf.ToMesh on an nx*ny*nz grid: cell layers [kb, ke)."""
+
+    def __init__(self, sdf, vmin, vmax, nx, ny, nz, kb, ke, clip=True, iso=0.0, step=1):
+        self.sdf = require_gpu_sdf(sdf)
+        self.ctx = self.sdf.ctx
+        self.min, self.max = numerics.vec3(vmin), numerics.vec3(vmax)
+        self.dims = (int(nx), int(ny), int(nz))
+        self.kb, self.ke, self.clip, self.iso, self.step = int(kb), int(ke), bool(clip), float(iso), int(step)
+        self.z0, self.z1 = slab_slices(self.kb, self.ke, self.step, self.dims[2])
+        self.vox = None
+        self.mesh = None
+        M, Nn = numerics.mesh_transforms(self.min, self.max, *self.dims)
+        self.M, self.Nn = N.f32c(M), N.f32c(Nn)
+
+    def sample(self):
+        """K1 on this rank's slices (allocates on first use, then re-samples in place)."""
+        L = N.lib()
+        if self.vox is None:
+            h = C.c_void_p()
+            nx, ny, nz = self.dims
+            N.check(L.sdfk_voxels_sample_slab(self.ctx.handle, self.sdf.handle, N.fptr(self.min), N.fptr(self.max), nx, ny, nz,
+                                              1 if self.clip else 0, self.z0, self.z1, C.byref(h)))
+            self.vox = h
+        else:
+            N.check(L.sdfk_voxels_resample(self.vox, self.sdf.handle, 1 if self.clip else 0))
+
+    def classify(self):
+        """K2-K4a; returns this rank's (vertices, triangles)."""
+        if self.mesh is not None:
+            self.mesh.destroy()
+        h = C.c_void_p()
+        nv, nt = C.c_int64(), C.c_int64()
+        N.check(N.lib().sdfk_mesh_classify(self.ctx.handle, self.vox, self.iso, self.step, self.kb, self.ke, C.byref(h),
+                                           C.byref(nv), C.byref(nt)))
+        self.mesh = GpuMesh(h)
+        return nv.value, nt.value
+
+    def emit(self, vertex_base, triangle_base):
+        """K4b with the global offsets fixed by the count all-gather."""
+        N.check(N.lib().sdfk_mesh_emit(self.mesh.handle, int(vertex_base), int(triangle_base), N.fptr(self.M), N.fptr(self.Nn)))
+        return self.mesh
+
+    def voxel_count(self):
+        """Voxels this rank owns for throughput accounting (halo slices are not counted)."""
+        nx, ny, nz = self.dims
+        zlo = self.kb * self.step
+        zhi = nz if self.ke >= cells_along(nz, self.step) else self.ke * self.step
+        return nx * ny * max(0, zhi - zlo)
+
+    def close(self):
+        if self.mesh is not None:
+            self.mesh.destroy()
+            self.mesh = None
+        if self.vox is not None:
+            N.lib().sdfk_voxels_destroy(self.vox)
+            self.vox = None
+
+
+def merge_meshes(parts):
+    """Concatenate per-slab meshes (already carrying global indices) in rank order -> Mesh."""
+    parts = [p for p in parts]
+    v = np.concatenate([p.Vertices for p in parts]) if parts else np.zeros((0, 3), np.float32)
+    c = np.concatenate([p.Colors for p in parts]) if parts else np.zeros((0, 3), np.float32)
+    n = np.concatenate([p.Normals for p in parts]) if parts else np.zeros((0, 3), np.float32)
+    t = np.concatenate([p.Triangles for p in parts]) if parts else np.zeros((0,), np.int32)
+    nonempty = [p for p in parts if len(p.Vertices)]
+    if nonempty:
+        mn = np.min(np.stack([p.Min for p in nonempty]), axis=0)
+        mx = np.max(np.stack([p.Max for p in nonempty]), axis=0)
+    else:
+        mn = mx = np.zeros(3, np.float32)
+    return Mesh(v, c, n, t, mn.astype(np.float32), mx.astype(np.float32))
+
+
+def to_mesh_by_slabs(sdf, vmin, vmax, nx, ny, nz, nslabs, clip=True, iso=0.0, step=1):
+    """Single-process emulation of an `nslabs`-rank job (the slabs run one after another on this GPU).  Used by
+    the tests to prove that the sharded result is identical to the single-GPU one."""
+    layers = partition(cells_along(nz, step), nslabs)
+    slabs = [SlabMesher(sdf, vmin, vmax, nx, ny, nz, kb, ke, clip, iso, step) for kb, ke in layers]
+    counts = []
+    for s in slabs:
+        s.sample()
+        counts.append(s.classify())
+    excl, _ = exclusive_offsets(counts)
+    parts = []
+    for s, (vb, tb) in zip(slabs, excl):
+        parts.append(s.emit(vb, tb).download())
+        s.close()
+    return merge_meshes(parts)
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.distributed plumbing (backend nccl on GPUs; gloo in the CPU tests)
+# ------------------------------------------------------------------------------------------------
+
+def all_gather_counts(nverts, ntris, device=None, group=None):
+    """The one data-path collective: all-gather (vertices, triangles) of every slab -> (excl[world,2], totals[2])."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.tensor([int(nverts), int(ntris)], dtype=torch.int64, device=device)
+    allc = torch.empty(world * 2, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    return exclusive_offsets(allc.cpu().numpy().reshape(world, 2))
+
+
+def gather_rows(local, counts, dst=0, group=None):
+    """Gather variable-length row blocks (a torch tensor per rank, same trailing shape) to `dst` with point-to-point
+    copies at the all-gathered offsets.  counts: rows per rank.  Returns the concatenated tensor on dst, else None."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    counts = [int(c) for c in counts]
+    if rank == dst:
+        out = torch.empty((sum(counts),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        ops = []
+        for r in range(world):
+            if counts[r] == 0:
+                continue
+            view = out[offs[r]:offs[r + 1]]
+            if r == dst:
+                view.copy_(local)
+            else:
+                ops.append(dist.P2POp(dist.irecv, view, r, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return out
+    if counts[rank] > 0:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst, group)]):
+            w.wait()
+    return None
+
+
+class DeviceArray:
+    """Zero-copy view of library-owned device memory for torch (`torch.as_tensor(DeviceArray(...), device='cuda')`)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def mesh_device_tensors(gpu_mesh, device):
+    """(vertices, colors, normals [nv,3] float32, triangles [nt,3] int32) aliasing the sdfk_mesh's device buffers."""
+    import torch
+    nv, nt = gpu_mesh.counts()
+    ptrs = [C.c_void_p() for _ in range(4)]
+    N.check(N.lib().sdfk_mesh_device_ptrs(gpu_mesh.handle, *[C.byref(p) for p in ptrs]))
+    out = []
+    for p, (rows, ts) in zip(ptrs, ((nv, "<f4"), (nv, "<f4"), (nv, "<f4"), (nt, "<i4"))):
+        if rows == 0 or not p.value:
+            out.append(torch.empty((0, 3), dtype=torch.float32 if ts == "<f4" else torch.int32, device=device))
+        else:
+            out.append(torch.as_tensor(DeviceArray(p.value, (rows, 3), ts), device=device))
+    return out

@@ -269,3 +269,54 @@ def test_render_row_bands_equal_full_image(sk):
     full = rm.Render().Array
     parts = [rm.Render(r0, r1).Array for r0, r1 in [(0, 23), (23, 46), (46, 69), (69, 90)]]
     assert_bits_equal(np.concatenate(parts), full, "row bands")
+
+
+# ---------------------------------------------------------------------------------------------- z-slab sharding
+
+@pytest.mark.parametrize("nslabs,step", [(2, 1), (3, 1), (8, 1), (2, 2)])
+def test_slab_sharded_mesh_equals_single_gpu(sk, oracle, nslabs, step):
+    """an N-rank z-slab job (emulated sequentially on one GPU: slab sampling with halo, ghost-layer
+    classification, offsets from the count exchange) must reproduce the single-GPU mesh exactly."""
+    from sdfkit_b200 import dist, scenes
+    expr, mn, mx = scenes.readme_scene()
+    sdf = expr.ToSdf()
+    n = 72
+    whole = sdf.ToMesh(mn, mx, n, n, n, step=step)
+    sharded = dist.to_mesh_by_slabs(sdf, mn, mx, n, n, n, nslabs, step=step)
+    assert len(whole.Vertices) > 0
+    assert np.array_equal(sharded.Triangles, whole.Triangles)
+    assert_bits_equal(sharded.Vertices, whole.Vertices, "slab vertices")
+    assert_bits_equal(sharded.Colors, whole.Colors, "slab colours")
+    assert_bits_equal(sharded.Normals, whole.Normals, "slab normals")
+    assert_bits_equal(sharded.Min, whole.Min, "slab aabb")
+    assert_bits_equal(sharded.Max, whole.Max, "slab aabb")
+
+
+def test_layer_ranges_on_white_noise(sk, oracle):
+    """Ghost-layer logic on the hardest input: mesh cell-layer ranges of a white-noise grid separately (all ambiguous
+    cases, centre vertices on slab boundaries) and compare the concatenation with the oracle's whole mesh."""
+    import ctypes as C
+    from sdfkit_b200 import _native as N, dist, numerics
+    rng = np.random.default_rng(21)
+    n = 30
+    vals = rng.uniform(-1, 1, (n, n, n)).astype(np.float32)
+    cols = rng.uniform(0, 1, (n, n, n, 3)).astype(np.float32)
+    vox = sk.Voxels(vals, cols, (-1, -1, -1), (1, 1, 1))
+    om = oracle.marching_cubes(vals, cols, np.float32([-1] * 3), np.float32([1] * 3))
+    M, Nn = numerics.mesh_transforms(vox.Min, vox.Max, n, n, n)
+    M, Nn = N.f32c(M), N.f32c(Nn)
+    ranges = [(0, 7), (7, 8), (8, 20), (20, 29)]
+    meshes, counts = [], []
+    for kb, ke in ranges:
+        h, nv, nt = C.c_void_p(), C.c_int64(), C.c_int64()
+        N.check(N.lib().sdfk_mesh_classify(vox.ctx.handle, vox.handle, 0.0, 1, kb, ke, C.byref(h), C.byref(nv), C.byref(nt)))
+        meshes.append(sk.GpuMesh(h))
+        counts.append((nv.value, nt.value))
+    excl, tot = dist.exclusive_offsets(counts)
+    assert tuple(tot) == (len(om.vertices), len(om.triangles))
+    parts = []
+    for m, (vb, tb) in zip(meshes, excl):
+        N.check(N.lib().sdfk_mesh_emit(m.handle, int(vb), int(tb), N.fptr(M), N.fptr(Nn)))
+        parts.append(m.download())
+    merged = dist.merge_meshes(parts)
+    assert_mesh_equal(merged, om, "white noise layer ranges")

@@ -1,0 +1,182 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every declared symbol, the SdfExpr
+lowering agrees with an independent numpy restatement, NVRTC accepts every scene, the System.Numerics
+restatement, and the sharding arithmetic (incl. a world_size-2 gloo run)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32 = np.float32
+
+
+def test_library_exports_every_declared_symbol():
+    from sdfkit_b200 import _native as N
+    header = open(os.path.join(ROOT, "include", "sdfk.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    declared = set(re.findall(r"\b(sdfk_[a-z0-9_]+)\s*\(", header)) - {"sdfk_progress_fn"}
+    assert declared, "no declarations parsed"
+    assert declared == set(N.SIGNATURES), sorted(declared ^ set(N.SIGNATURES))
+    L = N.lib()                      # binds (dlsym) every name in SIGNATURES
+    assert L.sdfk_version() >= 100
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import sdfkit_b200 as sk
+    with pytest.raises(sk.SdfkError, match="no CPU fallback"):
+        sk.Context()
+    with pytest.raises(sk.SdfkError):
+        sk.SdfExprs.Sphere(0.5).ToSdf()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sdfkit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")) and fn != "jit_embed.h":
+                text = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+                assert "oracle/" not in text and "sdfk_oracle" not in text, fn
+
+
+def _scenes():
+    from oracle import sdf_numpy as S
+    from sdfkit_b200 import scenes
+    return {
+        "sphere": (scenes.sphere()[0], S.sphere(0.5)),
+        "readme": (scenes.readme_scene()[0], S.readme_scene()),
+        "perf": (scenes.perf_scene()[0], S.perf_scene()),
+        "csg50": (scenes.csg50()[0], S.csg50(scenes.csg50_parts())),
+    }
+
+
+@pytest.mark.parametrize("name", ["sphere", "readme", "perf", "csg50"])
+def test_lowering_matches_numpy_restatement(oracle, name):
+    """The lowered dialect text (compiled by g++ here, by NVRTC on the GPU) against the numpy restatement written
+    independently from SdfExpr.cs -- bit for bit."""
+    expr, ref = _scenes()[name]
+    rng = np.random.default_rng(1)
+    pts = np.concatenate([rng.uniform(-4, 4, (20000, 3)), rng.normal(0, 0.6, (20000, 3)), np.zeros((1, 3))]).astype(np.float32)
+    a = oracle.eval_sdf(expr.Lower(), pts)
+    b = ref(pts)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["sphere", "readme", "perf", "csg50"])
+def test_nvrtc_accepts_every_scene(name):
+    """NVRTC compiles for sm_100a without a GPU: the JIT source (prelude + body + kernels) must build."""
+    from sdfkit_b200 import _native as N
+    expr, _ = _scenes()[name]
+    low = expr.Lower()
+    body = low.body.encode()
+    n = C.c_size_t()
+    N.check(N.lib().sdfk_sdf_check(body, len(body), C.byref(n)))
+    assert n.value > 1000
+    assert low.flops > 0
+    if name == "csg50":
+        assert low.node_count == 50
+
+
+def test_nvrtc_reports_bad_source():
+    from sdfkit_b200 import _native as N
+    body = b"    return not_a_function(p);\n"
+    rc = N.lib().sdfk_sdf_check(body, len(body), None)
+    assert rc == -3
+    assert b"not_a_function" in N.lib().sdfk_last_error()
+
+
+def test_exprs_semantics():
+    from sdfkit_b200.exprs import MathF, SdfExprs, Vector3, lower
+    # Union: strict <, ties pick b (SdfExpr.cs:63-66)
+    import oracle
+    a = SdfExprs.Sphere(0.5, (1, 0, 0))
+    b = SdfExprs.Sphere(0.5, (0, 1, 0))
+    out = oracle.eval_sdf(lower(SdfExprs.Union(a, b)), np.float32([[0.3, 0.1, 0.2]]))
+    assert tuple(out[0, :3]) == (0.0, 1.0, 0.0)
+    # opaque callables cannot be lowered
+    with pytest.raises(TypeError):
+        lower(lambda p: p)
+    # a symbolic value used in Python control flow is an error, not a silent constant
+    with pytest.raises(TypeError):
+        lower(SdfExprs.Solid(lambda p: 1.0 if p.X > 0 else 2.0))
+    # closure constants are folded in float32
+    low = lower(SdfExprs.Solid(lambda p: p.X * (f32(0.1) + f32(0.2))))
+    assert float(f32(0.1) + f32(0.2)).hex() in low.body
+
+
+def test_numerics_camera_and_mesh_transforms():
+    from sdfkit_b200 import numerics as nm
+    view = nm.create_look_at((0, 0, 5), (0, 0, 0), (0, 1, 0))
+    assert np.allclose(view, np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, -5, 1]], dtype=np.float32))
+    cam, ivp = nm.camera_matrices(view, 50, 30, 60.0, 1.0, 100.0)
+    assert np.allclose(cam, [0, 0, 5])
+    proj = nm.create_perspective_fov(np.float32(np.pi / 3), np.float32(50 / 30), 1.0, 100.0)
+    assert np.allclose(nm.multiply(nm.multiply(view, proj), ivp), np.eye(4), atol=1e-4)
+    assert abs(proj[2, 2] - (100.0 / (1.0 - 100.0))) < 1e-6 and proj[2, 3] == -1 and abs(proj[3, 2] - (100.0 / -99.0)) < 1e-6
+    M, Nn = nm.mesh_transforms((-1, -1, -1), (1, 1, 1), 64, 64, 64)
+    s = f32(2.0) / f32(63)
+    assert M[0, 0] == s and M[3, 0] == f32(-63 / 2.0) * s + f32(0)
+    assert np.allclose(Nn[:3, :3], np.eye(3) / s, rtol=1e-6)
+    a = np.float32(np.random.default_rng(0).uniform(-1, 1, (4, 4)))
+    assert np.allclose(nm.multiply(a, nm.invert(a)), np.eye(4), atol=1e-4)
+    assert nm.invert(np.zeros((4, 4), np.float32)) is None
+
+
+def test_sharding_arithmetic():
+    from sdfkit_b200 import dist
+    assert dist.cells_along(64, 1) == 63 and dist.cells_along(5, 2) == 2 and dist.cells_along(4, 2) == 1
+    assert dist.cells_along(1, 1) == 0 and dist.cells_along(2, 1) == 1
+    assert dist.partition(63, 4) == [(0, 16), (16, 32), (32, 48), (48, 63)]
+    assert dist.partition(3, 8) == [(0, 1), (1, 2), (2, 3)] + [(3, 3)] * 5
+    assert dist.slab_slices(0, 16, 1, 64) == (0, 18)       # bottom slab: no ghost below, one above
+    assert dist.slab_slices(16, 32, 1, 64) == (15, 34)
+    assert dist.slab_slices(48, 63, 1, 64) == (47, 64)     # top slab
+    assert dist.slab_slices(2, 4, 2, 12) == (2, 11)
+    excl, tot = dist.exclusive_offsets([[10, 20], [0, 0], [5, 7]])
+    assert excl.tolist() == [[0, 0], [10, 20], [10, 20]] and tot.tolist() == [15, 27]
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from sdfkit_b200 import dist as skd
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+counts = [(7, 11), (3, 5)]
+excl, tot = skd.all_gather_counts(*counts[rank])
+assert excl.tolist() == [[0, 0], [7, 11]] and tot.tolist() == [10, 16], (excl, tot)
+local = torch.arange(counts[rank][0] * 3, dtype=torch.float32).reshape(-1, 3) + 100 * rank
+out = skd.gather_rows(local, [c[0] for c in counts])
+if rank == 0:
+    assert out.shape == (10, 3) and out[7, 0].item() == 100.0 and out[6, 2].item() == 20.0
+else:
+    assert out is None
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_count_all_gather_and_mesh_gather_gloo_world2(tmp_path):
+    """The N>1 host path on CPU: world_size 2, gloo -- count all-gather -> offsets, variable-length gather to rank 0."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
