@@ -374,6 +374,7 @@ struct Mesher {
             for (int k = 0; k < 6; k++)
                 if (test_face(LUT[MCL_test13 + cfg * 7 + k])) sub += 1 << k;
             sub = LUT[MCL_subconfig13 + sub];
+            if (sub < 0) break;   // "Impossible case 13?" (MarchingCubes.cs:364-366): no triangles
             if (sub == 0) add_tris(ROW2(tiling13_1, cfg), 4);
             else if (sub <= 6) add_tris(ROW3(tiling13_2, cfg, sub - 1), 6);
             else if (sub <= 18) add_tris(ROW3(tiling13_3, cfg, sub - 7), 10);

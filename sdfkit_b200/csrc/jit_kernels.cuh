@@ -26,19 +26,25 @@ struct sdfk_sample_params {
     int clip;                  // ClipToBounds fused as a predicate
     int nx, ny, nz;            // dimensions of the WHOLE grid
     int z_begin;               // first z slice held by this slab
-    unsigned rows;             // ny * (slices in this slab)
+    int nzl;                   // slices in this slab
     unsigned tiles_per_row;    // ceil(nx / 128)
-    unsigned ntiles;           // rows * tiles_per_row
-    sdfk_fastdiv div_tpr, div_ny;
+    unsigned ncol;             // columns = tiles_per_row * ny
+    unsigned zsplit;           // z-segments per column (> 1 only when there are fewer columns than warps)
+    unsigned nwork;            // ncol * zsplit
+    sdfk_fastdiv div_tpr, div_ncol;
 };
 
 #define SDFK_SAMPLE_WARPS 8
 
 // Device layout (DESIGN.md "data layout"): x fastest.  dist[(zl*ny + y)*nx + x], rgb[((zl*ny + y)*nx + x)*3 + c],
-// zl = z - z_begin.  One warp handles a tile of 128 consecutive x of one row: every lane evaluates 4
-// consecutive voxels, the 4 distances leave as one float4 (512 B per warp store) and the 12 colour floats
-// are transposed through a warp-private shared-memory stage so that the 1536 B of colours also leave as
-// three fully coalesced 512 B float4 stores.  Streaming (evict-first) stores: the field is write-once.
+// zl = z - z_begin.  A warp owns a COLUMN -- 128 consecutive x of one y -- and walks it in z: everything
+// sdf_eval derives from p.x and p.y alone is loop-invariant and hoisted out of the z loop by the compiler (for
+// axis-separable trees such as RepeatXY that is nearly all of the arithmetic, including every IEEE division).
+// Per z step every lane evaluates 4 consecutive voxels; the 4 distances leave as one float4 (512 B per warp
+// store) and the 12 colour floats are transposed through a warp-private shared-memory stage so that the
+// 1536 B of colours also leave as three fully coalesced 512 B float4 stores.  Neighbouring warps hold
+// neighbouring columns, so at any moment the grid is writing a few contiguous planes.  Streaming
+// (evict-first) stores: the field is write-once.
 extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
 sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __restrict__ rgb)
 {
@@ -47,59 +53,68 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
     const unsigned warp = threadIdx.x >> 5;
     float4* const st = stage[warp];
     const bool vec = (P.nx & 3) == 0;
+    const size_t plane = (size_t)P.nx * (size_t)P.ny;
 
-    for (unsigned tile = blockIdx.x * SDFK_SAMPLE_WARPS + warp; tile < P.ntiles; tile += gridDim.x * SDFK_SAMPLE_WARPS) {
-        const unsigned row = sdfk_div(tile, P.div_tpr);
-        const unsigned xc = tile - row * P.tiles_per_row;
-        const unsigned zl = sdfk_div(row, P.div_ny);
-        const int iy = (int)(row - zl * (unsigned)P.ny);
-        const int iz = (int)zl + P.z_begin;
+    for (unsigned work = blockIdx.x * SDFK_SAMPLE_WARPS + warp; work < P.nwork; work += gridDim.x * SDFK_SAMPLE_WARPS) {
+        const unsigned seg = sdfk_div(work, P.div_ncol);
+        const unsigned col = work - seg * P.ncol;
+        const unsigned uy = sdfk_div(col, P.div_tpr);
+        const unsigned xc = col - uy * P.tiles_per_row;
+        const int iy = (int)uy;
+        const int zl0 = (int)(((long long)seg * P.nzl) / P.zsplit);
+        const int zl1 = (int)(((long long)(seg + 1) * P.nzl) / P.zsplit);
         const int x0 = (int)(xc * 128u + lane * 4u);
-
-        const float py = P.m1 + (float)iy * P.dy;     // p = min' + i*delta, one mul + one add (Voxels.cs:104-106)
-        const float pz = P.m2 + (float)iz * P.dz;
-        const bool yz_wall = P.clip && (iy == 0 || iy == P.ny - 1 || iz == 0 || iz == P.nz - 1);
-        const float fx0 = (float)x0;                  // exact; fx0 + k is exact below 2^24
-
-        float d[4];
-        float c[12];
+        const float fx0 = (float)x0;                               // exact; fx0 + k is exact below 2^24
+        const float py = P.m1 + (float)iy * P.dy;                  // p = min' + i*delta, one mul + one add (Voxels.cs:104-106)
+        const bool ywall = P.clip && (iy == 0 || iy == P.ny - 1);
+        float px[4];
+        bool xywall[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float px = P.m0 + (fx0 + (float)k) * P.dx;
-            const sk_float4 r = sdf_eval(sk_make3(px, py, pz));
-            const int ix = x0 + k;
-            const bool wall = yz_wall || (P.clip && (ix == 0 || ix == P.nx - 1));
-            d[k] = wall ? P.clip_value : r.w;
-            c[3 * k + 0] = r.x;
-            c[3 * k + 1] = r.y;
-            c[3 * k + 2] = r.z;
+            px[k] = P.m0 + (fx0 + (float)k) * P.dx;
+            xywall[k] = ywall || (P.clip && (x0 + k == 0 || x0 + k == P.nx - 1));
         }
+        const int nvalid = min(128, P.nx - (int)(xc * 128u));
+        const int nq = (nvalid * 3) >> 2;                          // float4s of colour per tile on the vector path
+        size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
 
-        const size_t vbase = (size_t)row * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
-        if (vec) {
-            const int nvalid = min(128, P.nx - (int)(xc * 128u));                // multiple of 4
-            if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
-            st[lane * 3 + 0] = make_float4(c[0], c[1], c[2], c[3]);
-            st[lane * 3 + 1] = make_float4(c[4], c[5], c[6], c[7]);
-            st[lane * 3 + 2] = make_float4(c[8], c[9], c[10], c[11]);
-            __syncwarp();
-            float4* const g = reinterpret_cast<float4*>(rgb + vbase * 3);
-            const int nq = (nvalid * 3) >> 2;                                    // float4s of colour in this tile
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int q = (int)lane + 32 * k;
-                if (q < nq) __stcs(g + q, st[q]);
-            }
-            __syncwarp();
-        } else {
+        for (int zl = zl0; zl < zl1; zl++, vbase += plane) {
+            const int iz = zl + P.z_begin;
+            const float pz = P.m2 + (float)iz * P.dz;
+            const bool zwall = P.clip && (iz == 0 || iz == P.nz - 1);
+            float d[4];
+            float c[12];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (x0 + k < P.nx) {
-                    const size_t v = vbase + lane * 4u + k;
-                    dist[v] = d[k];
-                    rgb[v * 3 + 0] = c[3 * k + 0];
-                    rgb[v * 3 + 1] = c[3 * k + 1];
-                    rgb[v * 3 + 2] = c[3 * k + 2];
+                const sk_float4 r = sdf_eval(sk_make3(px[k], py, pz));
+                d[k] = (zwall || xywall[k]) ? P.clip_value : r.w;
+                c[3 * k + 0] = r.x;
+                c[3 * k + 1] = r.y;
+                c[3 * k + 2] = r.z;
+            }
+            if (vec) {
+                if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
+                st[lane * 3 + 0] = make_float4(c[0], c[1], c[2], c[3]);
+                st[lane * 3 + 1] = make_float4(c[4], c[5], c[6], c[7]);
+                st[lane * 3 + 2] = make_float4(c[8], c[9], c[10], c[11]);
+                __syncwarp();
+                float4* const g = reinterpret_cast<float4*>(rgb + vbase * 3);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int q = (int)lane + 32 * k;
+                    if (q < nq) __stcs(g + q, st[q]);
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (x0 + k < P.nx) {
+                        const size_t v = vbase + lane * 4u + k;
+                        dist[v] = d[k];
+                        rgb[v * 3 + 0] = c[3 * k + 0];
+                        rgb[v * 3 + 1] = c[3 * k + 1];
+                        rgb[v * 3 + 2] = c[3 * k + 2];
+                    }
                 }
             }
         }

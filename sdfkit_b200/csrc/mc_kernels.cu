@@ -17,22 +17,35 @@
 //   K4b mc_emit     per record: triangle indices, created vertices (position, colour), normals gathered
 //                   in the reference's accumulation order, -normalize, Mesh.Transform, AABB
 #include <cstdio>
+#include <cstring>
 
 #include "mc_kernels.cuh"
 #include "mc_luts.h"
 
 #define MC_EPS 0.0000001                       // FLT_EPSILON of MarchingCubes.cs:37 / Cell.cs:65
 #define MC_AMBIG 0x80000000u
-#define MC_LEAF(off, nt, center) ((unsigned)(off) | ((unsigned)(nt) << 14) | ((unsigned)(center) << 18))
-#define MC_LEAF_OFF(l) ((l) & 0x3FFFu)
-#define MC_LEAF_NT(l) (((l) >> 14) & 0xFu)
-#define MC_LEAF_CENTER(l) (((l) >> 18) & 1u)
+// leaf = the tiling row a cell uses: dense row id [0:10) | triangles [10:14) | uses the centre vertex [14]
+#define MC_LEAF(row, nt, center) ((unsigned)(row) | ((unsigned)(nt) << 10) | ((unsigned)(center) << 14))
+#define MC_LEAF_ROW(l) ((l) & 0x3FFu)
+#define MC_LEAF_NT(l) (((l) >> 10) & 0xFu)
+#define MC_LEAF_CENTER(l) (((l) >> 14) & 1u)
 #define FULL 0xFFFFFFFFu
+
+// Static facts about one tiling row, precomputed on the host so that no kernel scans a row to answer them.
+struct McRowMeta {
+    unsigned short off;          // offset of the row's first entry in the LUT blob
+    unsigned char nt;            // triangles
+    unsigned char pad;
+    unsigned short refmask;      // slots (edges 0..11, centre 12) the row references
+    unsigned short before[13];   // before[e] = slots first referenced earlier in the row than e
+    unsigned char occ[13];       // how many times the row references slot e
+};
 
 static const signed char h_lut[MCL_BLOB_SIZE] = MCL_BLOB_INIT;
 __device__ const signed char d_lut[MCL_BLOB_SIZE] = MCL_BLOB_INIT;
 __device__ unsigned d_leaf[256];               // unambiguous cube index -> leaf, else MC_AMBIG
 __device__ unsigned short d_cross[256];        // cube index -> 12-bit mask of sign-changing edges
+__device__ McRowMeta d_meta[MCR_NROWS];
 
 // edge -> corner pair (Luts.cs:26-28 in corner numbering; MarchingCubes.cs:70-71)
 __host__ __device__ static inline void mc_edge_corners(int e, int& a, int& b)
@@ -45,17 +58,38 @@ __host__ __device__ static inline void mc_edge_corners(int e, int& a, int& b)
 
 cudaError_t mc_init_tables()
 {
-    unsigned leaf[256];
-    unsigned short cross[256];
-    // unambiguous Lewiner cases: tiling table offset, row length, triangle count (MarchingCubes.cs:98-372)
-    struct { int cas, off, len, nt; } simple[] = {
-        {1, MCL_tiling1, 3, 1}, {2, MCL_tiling2, 6, 2}, {5, MCL_tiling5, 9, 3}, {8, MCL_tiling8, 6, 2},
-        {9, MCL_tiling9, 12, 4}, {11, MCL_tiling11, 12, 4}, {14, MCL_tiling14, 12, 4}};
+    static unsigned leaf[256];
+    static unsigned short cross[256];
+    static McRowMeta meta[MCR_NROWS];
+    const struct { int off, rows, len; } tables[] = MCR_TABLES;
+    int rid = 0;
+    for (auto& t : tables) {
+        for (int r = 0; r < t.rows; r++, rid++) {
+            McRowMeta& m = meta[rid];
+            memset(&m, 0, sizeof(m));
+            m.off = (unsigned short)(t.off + r * t.len);
+            m.nt = (unsigned char)(t.len / 3);
+            unsigned seen = 0;
+            for (int k = 0; k < t.len; k++) {
+                const int e = h_lut[m.off + k];
+                if (e < 0 || e > 12) return cudaErrorInvalidValue;
+                if (!((seen >> e) & 1u)) m.before[e] = (unsigned short)seen;
+                seen |= 1u << e;
+                m.occ[e]++;
+            }
+            m.refmask = (unsigned short)seen;
+        }
+    }
+    if (rid != MCR_NROWS) return cudaErrorInvalidValue;
+    // unambiguous Lewiner cases: first row id of the tiling table, triangle count (MarchingCubes.cs:98-372)
+    const struct { int cas, row0, nt; } simple[] = {
+        {1, MCR_tiling1, 1}, {2, MCR_tiling2, 2}, {5, MCR_tiling5, 3}, {8, MCR_tiling8, 2},
+        {9, MCR_tiling9, 4}, {11, MCR_tiling11, 4}, {14, MCR_tiling14, 4}};
     for (int idx = 0; idx < 256; idx++) {
         int cas = h_lut[MCL_cases + idx * 2], cfg = h_lut[MCL_cases + idx * 2 + 1];
         leaf[idx] = (cas == 0) ? 0u : MC_AMBIG;
         for (auto& s : simple)
-            if (s.cas == cas) leaf[idx] = MC_LEAF(s.off + cfg * s.len, s.nt, 0);
+            if (s.cas == cas) leaf[idx] = MC_LEAF(s.row0 + cfg, s.nt, 0);
         unsigned m = 0;
         for (int e = 0; e < 12; e++) {
             int a, b;
@@ -65,8 +99,9 @@ cudaError_t mc_init_tables()
         cross[idx] = (unsigned short)m;
     }
     cudaError_t err = cudaMemcpyToSymbol(d_leaf, leaf, sizeof(leaf));
-    if (err != cudaSuccess) return err;
-    return cudaMemcpyToSymbol(d_cross, cross, sizeof(cross));
+    if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_cross, cross, sizeof(cross));
+    if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_meta, meta, sizeof(meta));
+    return err;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -151,8 +186,8 @@ __device__ static bool mc_test_internal(const double* v, int cas, int cfg, int s
     return s < 0;
 }
 
-#define LEAF2(name, cfg, nt, center) MC_LEAF(MCL_##name + (cfg) * MCL_##name##_D1, nt, center)
-#define LEAF3(name, cfg, sub, nt, center) MC_LEAF(MCL_##name + ((cfg) * MCL_##name##_D1 + (sub)) * MCL_##name##_D2, nt, center)
+#define LEAF2(name, cfg, nt, center) MC_LEAF(MCR_##name + (cfg), nt, center)
+#define LEAF3(name, cfg, sub, nt, center) MC_LEAF(MCR_##name + (cfg) * MCL_##name##_D1 + (sub), nt, center)
 
 // MarchingCubes.TheBigSwitch for the ambiguous cases (MarchingCubes.cs:105-366): chooses the tiling row.
 // v[k] = (double)value_k - (double)iso in the reference's corner numbering.
@@ -202,6 +237,7 @@ __device__ __noinline__ static unsigned mc_resolve(int idx, const double* v)
         for (int k = 0; k < 6; k++)
             if (mc_test_face(v, d_lut[MCL_test13 + cfg * 7 + k])) sub += 1 << k;
         sub = d_lut[MCL_subconfig13 + sub];
+        if (sub < 0) return MC_LEAF(0, 0, 0);   // "Impossible case 13?" (MarchingCubes.cs:364-366): no triangles
         if (sub == 0) return LEAF2(tiling13_1, cfg, 4, 0);
         if (sub <= 6) return LEAF3(tiling13_2, cfg, sub - 1, 6, 0);
         if (sub <= 18) return LEAF3(tiling13_3, cfg, sub - 7, 10, 1);
@@ -283,10 +319,69 @@ __device__ static inline unsigned mc_cell_leaf(const McGrid& g, const float* __r
     return leaf;
 }
 
+// packed (active, created vertices, triangles) of an active cell; a cell whose leaf has no triangles (the
+// reference's "impossible" case 13) emits nothing and is not recorded
 __device__ static inline unsigned mc_cell_counts(unsigned leaf, int idx, int i, int j, int kg)
 {
+    if (MC_LEAF_NT(leaf) == 0u) return 0u;
     const unsigned nv = __popc((unsigned)d_cross[idx] & mc_owned_mask(i, j, kg)) + MC_LEAF_CENTER(leaf);
     return MC_CNT_PACK(1, nv, MC_LEAF_NT(leaf));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sign rows: 5 sign bits for voxels (i0..i0+4)*step of one voxel row: bit t = value > iso (strict, Cell.cs:221-228;
+// the float compare is exact for (double)value - (double)iso > 0).  Loads are issued branch-free (addresses
+// clamped into the row) so that a whole batch of rows is in flight before the first compare.
+// ---------------------------------------------------------------------------------------------------
+struct McRowLoad {
+    float4 q;      // VEC: voxels i0..i0+3 ; generic: t = 0..3
+    float e;       // VEC: voxel i0+4 for lane 31 (own voxel i0+3 for the other lanes: same sector) ; generic: t = 4
+};
+
+template <bool VEC>
+__device__ static inline McRowLoad mc_row_load(const float* __restrict__ row, int nx, int step, int i0, unsigned lane)
+{
+    McRowLoad r;
+    if (VEC) {   // step == 1, nx % 4 == 0: one 16-byte load per lane (+ the right neighbour for lane 31)
+        const int ic = min(i0, nx - 4);
+        r.q = __ldg(reinterpret_cast<const float4*>(row + ic));
+        r.e = __ldg(row + ic + ((lane == 31u && i0 + 4 < nx) ? 4 : 3));
+    } else {
+        const long long last = nx - 1;
+        r.q.x = __ldg(row + min((long long)(i0 + 0) * step, last));
+        r.q.y = __ldg(row + min((long long)(i0 + 1) * step, last));
+        r.q.z = __ldg(row + min((long long)(i0 + 2) * step, last));
+        r.q.w = __ldg(row + min((long long)(i0 + 3) * step, last));
+        r.e = __ldg(row + min((long long)(i0 + 4) * step, last));
+    }
+    return r;
+}
+
+template <bool VEC>
+__device__ static inline unsigned mc_row_bits(const McRowLoad& r, float iso, int nx, int step, int i0, unsigned lane)
+{
+    unsigned s = (r.q.x > iso ? 1u : 0u) | (r.q.y > iso ? 2u : 0u) | (r.q.z > iso ? 4u : 0u) | (r.q.w > iso ? 8u : 0u);
+    if (VEC) {
+        if (i0 >= nx) s = 0u;
+        unsigned nb = __shfl_down_sync(FULL, s, 1) & 1u;
+        if (lane == 31u) nb = (i0 + 4 < nx && r.e > iso) ? 1u : 0u;
+        s |= nb << 4;
+    } else {
+        s |= (r.e > iso ? 16u : 0u);
+        unsigned valid = 0;
+#pragma unroll
+        for (int t = 0; t < 5; t++)
+            if ((long long)(i0 + t) * step < nx) valid |= 1u << t;
+        s &= valid;
+    }
+    return s;
+}
+
+// cube index of cell c (0..3) of a lane from the 5-bit sign rows (lo = plane z, hi = plane z+step; 0 = row y, 1 = row y+step)
+__device__ static inline int mc_cube_index(unsigned lo0, unsigned lo1, unsigned hi0, unsigned hi1, int c)
+{
+    return (int)(((lo0 >> c) & 3u) | (((lo1 >> (c + 1)) & 1u) << 2) | (((lo1 >> c) & 1u) << 3) |
+                 (((hi0 >> c) & 3u) << 4) | (((hi1 >> (c + 1)) & 1u) << 6) | (((hi1 >> c) & 1u) << 7));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -297,29 +392,15 @@ __device__ static inline unsigned mc_cell_counts(unsigned leaf, int idx, int i, 
 #define MC_K 16
 #define MC_CLASSIFY_WARPS 8
 
-// 5 sign bits for voxels (i0..i0+4)*step of voxel row (y, zl): bit t = value > iso (strict, Cell.cs:221-228;
-// float compare is exact for (double)value - (double)iso > 0)
 template <bool VEC>
-__device__ static inline unsigned mc_row_signs(const McGrid& g, const float* __restrict__ dist, int i0, int y, int zl, unsigned lane)
+__device__ static inline void mc_plane_signs(const float* __restrict__ plane, size_t row_stride, int nrows, int nx, int step,
+                                             float iso, int i0, unsigned lane, unsigned* out)
 {
-    const float* row = dist + ((size_t)zl * g.ny + y) * (size_t)g.nx;
-    unsigned s = 0;
-    if (VEC) {   // step == 1, nx % 4 == 0: one 16-byte load per lane, neighbour bit by shuffle
-        if (i0 < g.nx) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(row + i0));
-            s = (q.x > g.iso ? 1u : 0u) | (q.y > g.iso ? 2u : 0u) | (q.z > g.iso ? 4u : 0u) | (q.w > g.iso ? 8u : 0u);
-        }
-        unsigned nb = __shfl_down_sync(FULL, s, 1) & 1u;
-        if (lane == 31) nb = (i0 + 4 < g.nx) ? (__ldg(row + i0 + 4) > g.iso ? 1u : 0u) : 0u;
-        s |= nb << 4;
-    } else {
+    McRowLoad ld[MC_R + 1];
 #pragma unroll
-        for (int t = 0; t < 5; t++) {
-            const long long x = (long long)(i0 + t) * g.step;
-            if (x < g.nx && __ldg(row + x) > g.iso) s |= 1u << t;
-        }
-    }
-    return s;
+    for (int r = 0; r <= MC_R; r++) ld[r] = mc_row_load<VEC>(plane + (size_t)min(r, nrows) * row_stride, nx, step, i0, lane);
+#pragma unroll
+    for (int r = 0; r <= MC_R; r++) out[r] = mc_row_bits<VEC>(ld[r], iso, nx, step, i0, lane);
 }
 
 template <bool VEC>
@@ -330,54 +411,48 @@ mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __r
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = blockIdx.x * MC_CLASSIFY_WARPS + (threadIdx.x >> 5);
     const unsigned nw = gridDim.x * MC_CLASSIFY_WARPS;
+    const int nx = g.nx, step = g.step, ncx = g.ncx, ncy = g.ncy, cpr = g.cpr;
+    const float iso = g.iso;
+    const size_t row_stride = (size_t)step * (size_t)nx;                // floats between voxel rows y and y+step
+    const size_t plane_stride = (size_t)g.ny * (size_t)nx;              // floats per z slice
     for (unsigned tile = gw; tile < ntiles; tile += nw) {
         // tile -> (xc fastest, then row block, then layer block): neighbouring warps read neighbouring segments
-        const unsigned xc = tile % (unsigned)g.cpr;
-        const unsigned t2 = tile / (unsigned)g.cpr;
+        const unsigned xc = tile % (unsigned)cpr;
+        const unsigned t2 = tile / (unsigned)cpr;
         const unsigned jb = t2 % njb;
         const unsigned kb = t2 / njb;
         const int i0 = (int)(xc * 128u + lane * 4u);
         const int j0 = (int)(jb * MC_R);
-        const int kl0 = (int)(kb * MC_K);                     // local layer index
-        const int nrows = min(MC_R, g.ncy - j0);
+        const int kl0 = (int)(kb * MC_K);                               // local layer index
+        const int nrows = min(MC_R, ncy - j0);
         const int nlay = min(MC_K, g.nk - kl0);
+        const float* plane = dist + (size_t)((g.k0 + kl0) * step - g.z0) * plane_stride + (size_t)j0 * row_stride;
+        unsigned* cnt_out = counts + ((size_t)kl0 * ncy + j0) * cpr + xc;
 
         unsigned prev[MC_R + 1], cur[MC_R + 1];
-        {
-            const int zl = (g.k0 + kl0) * g.step - g.z0;
-#pragma unroll
-            for (int r = 0; r <= MC_R; r++)
-                prev[r] = (r <= nrows) ? mc_row_signs<VEC>(g, dist, i0, (j0 + r) * g.step, zl, lane) : 0u;
-        }
+        mc_plane_signs<VEC>(plane, row_stride, nrows, nx, step, iso, i0, lane, prev);
         for (int kk = 0; kk < nlay; kk++) {
+            plane += (size_t)step * plane_stride;
+            mc_plane_signs<VEC>(plane, row_stride, nrows, nx, step, iso, i0, lane, cur);
             const int kg = g.k0 + kl0 + kk;
-            const int zl = (kg + 1) * g.step - g.z0;
-#pragma unroll
-            for (int r = 0; r <= MC_R; r++)
-                cur[r] = (r <= nrows) ? mc_row_signs<VEC>(g, dist, i0, (j0 + r) * g.step, zl, lane) : 0u;
 #pragma unroll
             for (int r = 0; r < MC_R; r++) {
-                if (r < nrows) {
-                    const unsigned lo0 = prev[r], lo1 = prev[r + 1], hi0 = cur[r], hi1 = cur[r + 1];
-                    unsigned cnt = 0;
-                    const unsigned any = lo0 | lo1 | hi0 | hi1, all = lo0 & lo1 & hi0 & hi1;
-                    if (any != 0u && all != 31u) {
-                        const int j = j0 + r;
+                const unsigned lo0 = prev[r], lo1 = prev[r + 1], hi0 = cur[r], hi1 = cur[r + 1];
+                unsigned cnt = 0;
+                const unsigned any = lo0 | lo1 | hi0 | hi1, all = lo0 & lo1 & hi0 & hi1;
+                if (any != 0u && all != 31u && r < nrows) {             // rare: the lane's 4 cells are not all empty / all full
+                    const int j = j0 + r;
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            const int idx = (int)(((lo0 >> c) & 3u) | (((lo1 >> (c + 1)) & 1u) << 2) | (((lo1 >> c) & 1u) << 3) |
-                                                  (((hi0 >> c) & 3u) << 4) | (((hi1 >> (c + 1)) & 1u) << 6) | (((hi1 >> c) & 1u) << 7));
-                            const int i = i0 + c;
-                            if (i < g.ncx && idx != 0 && idx != 255) {
-                                const unsigned leaf = mc_cell_leaf(g, dist, idx, i, j, kg);
-                                cnt += mc_cell_counts(leaf, idx, i, j, kg);
-                            }
-                        }
+                    for (int c = 0; c < 4; c++) {
+                        const int idx = mc_cube_index(lo0, lo1, hi0, hi1, c);
+                        const int i = i0 + c;
+                        if (i < ncx && idx != 0 && idx != 255) cnt += mc_cell_counts(mc_cell_leaf(g, dist, idx, i, j, kg), idx, i, j, kg);
                     }
-                    const unsigned total = __reduce_add_sync(FULL, cnt);
-                    if (lane == 0) counts[((size_t)(kl0 + kk) * g.ncy + (j0 + r)) * g.cpr + xc] = total;
                 }
+                const unsigned total = __reduce_add_sync(FULL, cnt);
+                if (lane == 0 && r < nrows) cnt_out[(size_t)r * cpr] = total;
             }
+            cnt_out += (size_t)ncy * cpr;
 #pragma unroll
             for (int r = 0; r <= MC_R; r++) prev[r] = cur[r];
         }
@@ -397,7 +472,7 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
     unsigned blocks = (ntiles + MC_CLASSIFY_WARPS - 1) / MC_CLASSIFY_WARPS;
     const unsigned maxb = (unsigned)sms * 8u;
     if (blocks > maxb) blocks = maxb;
-    const bool vec = g.step == 1 && (g.nx & 3) == 0;
+    const bool vec = g.step == 1 && (g.nx & 3) == 0 && g.nx >= 4;
     if (vec) mc_classify_kernel<true><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
     else mc_classify_kernel<false><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
     return cudaGetLastError();
@@ -528,15 +603,22 @@ cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4a mc_compact: re-classify the active chunks and write one record per active cell, in visiting order
+// K4a mc_compact: re-classify the active chunks and write one record per active cell, in visiting order,
+// plus the chunk's 128-bit activity mask (4 ballots: bit l of word c <-> cell 4*l + c) that makes the
+// record of any cell an O(1) lookup:  base[chunk].x + rank(mask, cell).
 // ---------------------------------------------------------------------------------------------------
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned* __restrict__ counts,
-                  const uint4* __restrict__ base, McRecord* __restrict__ recs)
+                  const uint4* __restrict__ base, McRecord* __restrict__ recs, uint4* __restrict__ masks)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    const int nx = g.nx, step = g.step;
+    const float iso = g.iso;
+    const size_t row_stride = (size_t)step * (size_t)nx;
+    const size_t plane_stride = (size_t)g.ny * (size_t)nx;
     for (unsigned c0 = gw * 32u; c0 < g.nchunks; c0 += nw * 32u) {
         const unsigned mine = (c0 + lane < g.nchunks) ? MC_CNT_ACT(counts[c0 + lane]) : 0u;
         unsigned todo = __ballot_sync(FULL, mine != 0u);
@@ -549,27 +631,30 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
             const int kl = (int)(row / (unsigned)g.ncy);
             const int kg = g.k0 + kl;
             const int i0 = (int)(xc * 128u + lane * 4u);
-            unsigned leaf[4];
-            unsigned cnt[4];
+            const float* p00 = dist + (size_t)(kg * step - g.z0) * plane_stride + (size_t)j * row_stride;
+            const McRowLoad l00 = mc_row_load<VEC>(p00, nx, step, i0, lane);
+            const McRowLoad l01 = mc_row_load<VEC>(p00 + row_stride, nx, step, i0, lane);
+            const McRowLoad l10 = mc_row_load<VEC>(p00 + (size_t)step * plane_stride, nx, step, i0, lane);
+            const McRowLoad l11 = mc_row_load<VEC>(p00 + (size_t)step * plane_stride + row_stride, nx, step, i0, lane);
+            const unsigned lo0 = mc_row_bits<VEC>(l00, iso, nx, step, i0, lane), lo1 = mc_row_bits<VEC>(l01, iso, nx, step, i0, lane);
+            const unsigned hi0 = mc_row_bits<VEC>(l10, iso, nx, step, i0, lane), hi1 = mc_row_bits<VEC>(l11, iso, nx, step, i0, lane);
+            unsigned leaf[4], cnt[4];
             unsigned tot = 0;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 leaf[c] = 0;
                 cnt[c] = 0;
+                const int idx = mc_cube_index(lo0, lo1, hi0, hi1, c);
                 const int i = i0 + c;
-                if (i < g.ncx) {
-                    double v[8];
-                    mc_load_cell(g, dist, i, j, kg, v);
-                    const int idx = mc_index_of(v);
-                    if (idx != 0 && idx != 255) {
-                        unsigned lf = d_leaf[idx];
-                        if (lf & MC_AMBIG) lf = mc_resolve(idx, v);
-                        leaf[c] = lf;
-                        cnt[c] = mc_cell_counts(lf, idx, i, j, kg);
-                    }
+                if (i < g.ncx && idx != 0 && idx != 255) {
+                    leaf[c] = mc_cell_leaf(g, dist, idx, i, j, kg);
+                    cnt[c] = mc_cell_counts(leaf[c], idx, i, j, kg);
                 }
                 tot += cnt[c];
             }
+            const uint4 m = make_uint4(__ballot_sync(FULL, cnt[0] != 0u), __ballot_sync(FULL, cnt[1] != 0u),
+                                       __ballot_sync(FULL, cnt[2] != 0u), __ballot_sync(FULL, cnt[3] != 0u));
+            if (lane == 0) masks[chunk] = m;
             // exclusive warp scan of the packed (act | verts | tris) counts; fields cannot overflow inside a chunk
             unsigned inc = tot;
 #pragma unroll
@@ -596,7 +681,7 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
 }
 
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
-                              McRecord* recs, cudaStream_t s)
+                              McRecord* recs, uint4* masks, cudaStream_t s)
 {
     if (g.nchunks == 0) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -605,47 +690,36 @@ cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned
     unsigned groups = (g.nchunks + 31u) / 32u;
     unsigned blocks = (groups + 7u) / 8u;
     if (blocks > (unsigned)sms * 8u) blocks = (unsigned)sms * 8u;
-    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, counts, base, recs);
+    const bool vec = g.step == 1 && (g.nx & 3) == 0 && g.nx >= 4;
+    if (vec) mc_compact_kernel<true><<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks);
+    else mc_compact_kernel<false><<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4b mc_emit
+// K4b mc_emit: one thread per active cell
 // ---------------------------------------------------------------------------------------------------
 
-// record of cell (i, j, kl) -- must exist
+// index of the record of cell (i, j, kl), -1 if that cell is not active
 __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j, int kl)
 {
     const McGrid& g = p.g;
     const unsigned chunk = ((unsigned)kl * (unsigned)g.ncy + (unsigned)j) * (unsigned)g.cpr + ((unsigned)i >> 7);
-    const uint4 b = p.base[chunk];
-    const unsigned cell = (unsigned)i + (unsigned)g.ncx * ((unsigned)j + (unsigned)g.ncy * (unsigned)kl);
-    int lo = (int)b.x, hi = (int)(b.x + MC_CNT_ACT(b.w)) - 1;
-    while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        const unsigned c = p.recs[mid].cell;
-        if (c == cell) return mid;
-        if (c < cell) lo = mid + 1;
-        else hi = mid - 1;
-    }
-    return -1;
+    const uint4 b = __ldg(p.base + chunk);
+    if (MC_CNT_ACT(b.w) == 0u) return -1;
+    const uint4 m = __ldg(p.masks + chunk);
+    const unsigned l = ((unsigned)i & 127u) >> 2, c = (unsigned)i & 3u;
+    const unsigned w[4] = {m.x, m.y, m.z, m.w};
+    if (!((w[c] >> l) & 1u)) return -1;
+    const unsigned below = (1u << l) - 1u;
+    unsigned rank = __popc(m.x & below) + __popc(m.y & below) + __popc(m.z & below) + __popc(m.w & below);
+    if (c > 0) rank += (m.x >> l) & 1u;
+    if (c > 1) rank += (m.y >> l) & 1u;
+    if (c > 2) rank += (m.z >> l) & 1u;
+    return (int)(b.x + rank);
 }
 
-// position of slot e in the creation order of a cell: number of distinct created slots first seen before it
-__device__ static inline int mc_rank_in_row(const signed char* row, int nent, unsigned owned, int e)
-{
-    unsigned seen = 0;
-    int rank = 0;
-    for (int k = 0; k < nent; k++) {
-        const int q = row[k];
-        if (q == e) return rank;
-        const unsigned bit = 1u << q;
-        if ((owned & bit) && !(seen & bit)) { seen |= bit; rank++; }
-    }
-    return -1;
-}
-
-// (float) gradient row `r` (ORIGINAL corner numbering, Cell.cs:491-498) component a = v[p] - v[q]
+// gradient row `r` (ORIGINAL corner numbering, Cell.cs:491-498), component a: v[p] - v[q]
 __device__ static inline double mc_vg(const double* v, int r, int a)
 {
     // 8 rows x 3 components, (p,q) packed 3 bits each
@@ -664,15 +738,23 @@ __device__ static inline double mc_vg(const double* v, int r, int a)
 
 struct McF3 { float x, y, z; };
 
+// end corners of edge e as positional indices dz*4 + dy*2 + dx (Luts.cs:26-28, Cell.cs:303-308)
+__device__ static inline void mc_edge_ends(int e, int& i1, int& i2)
+{
+    // (dx,dy,dz) pairs of EDGETORELATIVEPOS{X,Y,Z}: packed i1 | i2 << 3
+    const unsigned char tab[12] = {0 | 1 << 3, 1 | 3 << 3, 3 | 2 << 3, 2 | 0 << 3, 4 | 5 << 3, 5 | 7 << 3,
+                                   7 | 6 << 3, 6 | 4 << 3, 0 | 4 << 3, 1 | 5 << 3, 3 | 7 << 3, 2 | 6 << 3};
+    i1 = tab[e] & 7;
+    i2 = tab[e] >> 3;
+}
+
 // adds, for `times` references of local edge e in a sharing cell, the two end-corner gradient contributions
 // exactly like Cell.AddGradientFromIndex (Cell.cs:154-158,331-333): note vg is indexed with the dz*4+dy*2+dx
 // corner index although its rows are in the v0..v7 numbering -- a quirk of the reference that is preserved.
 __device__ static inline void mc_add_edge_gradients(const double* v, int e, int times, McF3& n)
 {
-    const int dx1 = d_lut[MCL_edgesrelx + e * 2], dx2 = d_lut[MCL_edgesrelx + e * 2 + 1];
-    const int dy1 = d_lut[MCL_edgesrely + e * 2], dy2 = d_lut[MCL_edgesrely + e * 2 + 1];
-    const int dz1 = d_lut[MCL_edgesrelz + e * 2], dz2 = d_lut[MCL_edgesrelz + e * 2 + 1];
-    const int i1 = dz1 * 4 + dy1 * 2 + dx1, i2 = dz2 * 4 + dy2 * 2 + dx2;
+    int i1, i2;
+    mc_edge_ends(e, i1, i2);
     const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};                     // vv[] re-ordering (Cell.cs:453-460)
     const double w1 = 1.0 / (MC_EPS + fabs(v[ro[i1]]));
     const double w2 = 1.0 / (MC_EPS + fabs(v[ro[i2]]));
@@ -690,7 +772,7 @@ __device__ static inline unsigned mc_float_key(float f)   // monotonic float -> 
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ static inline void mc_store_vertex(const McEmitParams& p, long long slot, McF3 pos, McF3 col, McF3 nsum)
+__device__ static inline void mc_store_vertex(const McEmitParams& p, long long slot, McF3 pos, McF3 col, McF3 nsum, unsigned* lo, unsigned* hi)
 {
     // Cell.NegativeNormals (Cell.cs:97-109): -Vector3.Normalize(sum)
     const float len = sqrtf((nsum.x * nsum.x + nsum.y * nsum.y) + nsum.z * nsum.z);
@@ -712,13 +794,9 @@ __device__ static inline void mc_store_vertex(const McEmitParams& p, long long s
     vo[0] = pos.x; vo[1] = pos.y; vo[2] = pos.z;
     co[0] = col.x; co[1] = col.y; co[2] = col.z;
     no[0] = n.x; no[1] = n.y; no[2] = n.z;
-    // Mesh.Measure (Mesh.cs:30-45)
-    atomicMin(p.aabb_keys + 0, mc_float_key(pos.x));
-    atomicMin(p.aabb_keys + 1, mc_float_key(pos.y));
-    atomicMin(p.aabb_keys + 2, mc_float_key(pos.z));
-    atomicMax(p.aabb_keys + 3, mc_float_key(pos.x));
-    atomicMax(p.aabb_keys + 4, mc_float_key(pos.y));
-    atomicMax(p.aabb_keys + 5, mc_float_key(pos.z));
+    // Mesh.Measure (Mesh.cs:30-45), reduced per thread -> per warp -> one atomic per warp
+    lo[0] = min(lo[0], mc_float_key(pos.x)); lo[1] = min(lo[1], mc_float_key(pos.y)); lo[2] = min(lo[2], mc_float_key(pos.z));
+    hi[0] = max(hi[0], mc_float_key(pos.x)); hi[1] = max(hi[1], mc_float_key(pos.y)); hi[2] = max(hi[2], mc_float_key(pos.z));
 }
 
 __global__ void __launch_bounds__(128)
@@ -726,157 +804,153 @@ mc_emit_kernel(const McEmitParams p)
 {
     const McGrid& g = p.g;
     const unsigned r = p.rec_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.rec_end) return;
-    const McRecord rec = p.recs[r];
-    const int i = (int)(rec.cell % (unsigned)g.ncx);
-    const unsigned t2 = rec.cell / (unsigned)g.ncx;
-    const int j = (int)(t2 % (unsigned)g.ncy);
-    const int kl = (int)(t2 / (unsigned)g.ncy);
-    const int kg = g.k0 + kl;
-    const signed char* row = d_lut + MC_LEAF_OFF(rec.info);
-    const int nt = (int)MC_LEAF_NT(rec.info);
-    const int nent = 3 * nt;
-    const unsigned owned = mc_owned_mask(i, j, kg);
+    unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    if (r < p.rec_end) {
+        const McRecord rec = p.recs[r];
+        const int i = (int)(rec.cell % (unsigned)g.ncx);
+        const unsigned t2 = rec.cell / (unsigned)g.ncx;
+        const int j = (int)(t2 % (unsigned)g.ncy);
+        const int kl = (int)(t2 / (unsigned)g.ncy);
+        const int kg = g.k0 + kl;
+        const McRowMeta* meta = d_meta + MC_LEAF_ROW(rec.info);
+        const signed char* row = d_lut + meta->off;
+        const int nent = 3 * (int)MC_LEAF_NT(rec.info);
+        const unsigned owned = mc_owned_mask(i, j, kg);
+        const unsigned refd = meta->refmask;
 
-    double v[8];
-    mc_load_cell(g, p.dist, i, j, kg, v);
+        double v[8];
+        mc_load_cell(g, p.dist, i, j, kg, v);
 
-    // ---- vertex id of every slot this cell references
-    unsigned refd = 0;
-    for (int k = 0; k < nent; k++) refd |= 1u << row[k];
-    long long vid[13];
-    for (int e = 0; e < 13; e++) {
-        if (!((refd >> e) & 1u)) continue;
-        if ((owned >> e) & 1u) {
-            vid[e] = (long long)(rec.vbase + (unsigned)mc_rank_in_row(row, nent, owned, e));
-            continue;
+        // ---- vertex id of every slot this cell references
+        int vid[13];
+        for (unsigned todo = refd; todo; todo &= todo - 1) {
+            const int e = __ffs(todo) - 1;
+            if ((owned >> e) & 1u) {
+                vid[e] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[e] & owned));
+                continue;
+            }
+            // creator = sharing cell smallest in (k, j, i); e2 = the edge's id in the creator's numbering
+            int di = 0, dj = 0, dk = 0, e2 = e;
+            switch (e) {
+            case 0: dk = kg > 0 ? -1 : 0; dj = j > 0 ? -1 : 0; e2 = dk ? (dj ? 6 : 4) : (dj ? 2 : 0); break;
+            case 1: dk = -1; e2 = 5; break;
+            case 2: dk = -1; e2 = 6; break;
+            case 3: dk = kg > 0 ? -1 : 0; di = i > 0 ? -1 : 0; e2 = dk ? (di ? 5 : 7) : (di ? 1 : 3); break;
+            case 4: dj = -1; e2 = 6; break;
+            case 7: di = -1; e2 = 5; break;
+            case 8: if (j > 0) { dj = -1; if (i > 0) { di = -1; e2 = 10; } else e2 = 11; } else { di = -1; e2 = 9; } break;
+            case 9: dj = -1; e2 = 10; break;
+            case 11: di = -1; e2 = 10; break;
+            }
+            const int oi = i + di, oj = j + dj, okl = kl + dk;
+            const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl) : -1;
+            if (orr < 0) { atomicExch(p.error_flag, 1); vid[e] = 0; continue; }
+            const McRecord orec = p.recs[orr];
+            const McRowMeta* om = d_meta + MC_LEAF_ROW(orec.info);
+            if (!((om->refmask >> e2) & 1u)) { atomicExch(p.error_flag, 2); vid[e] = 0; continue; }
+            vid[e] = (int)(orec.vbase + (unsigned)__popc((unsigned)om->before[e2] & mc_owned_mask(oi, oj, kg + dk)));
         }
-        // creator = sharing cell smallest in (k, j, i); e2 = the edge's id in the creator's numbering
-        int di = 0, dj = 0, dk = 0, e2 = e;
-        switch (e) {
-        case 0: dk = kg > 0 ? -1 : 0; dj = j > 0 ? -1 : 0; e2 = dk ? (dj ? 6 : 4) : (dj ? 2 : 0); break;
-        case 1: dk = -1; e2 = 5; break;
-        case 2: dk = -1; e2 = 6; break;
-        case 3: dk = kg > 0 ? -1 : 0; di = i > 0 ? -1 : 0; e2 = dk ? (di ? 5 : 7) : (di ? 1 : 3); break;
-        case 4: dj = -1; e2 = 6; break;
-        case 7: di = -1; e2 = 5; break;
-        case 8: if (j > 0) { dj = -1; if (i > 0) { di = -1; e2 = 10; } else e2 = 11; } else { di = -1; e2 = 9; } break;
-        case 9: dj = -1; e2 = 10; break;
-        case 11: di = -1; e2 = 10; break;
+        // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
+        {
+            int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
+            const int shift = (int)(p.vglobal0 - (long long)p.vlocal0);
+            for (int k = 0; k < nent; k++) out[k] = vid[row[k]] + shift;
         }
-        const int oi = i + di, oj = j + dj, okl = kl + dk;
-        const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl) : -1;
-        if (orr < 0) { atomicExch(p.error_flag, 1); vid[e] = 0; continue; }
-        const McRecord orec = p.recs[orr];
-        const int rk = mc_rank_in_row(d_lut + MC_LEAF_OFF(orec.info), 3 * (int)MC_LEAF_NT(orec.info), mc_owned_mask(oi, oj, kg + dk), e2);
-        if (rk < 0) { atomicExch(p.error_flag, 2); vid[e] = 0; continue; }
-        vid[e] = (long long)(orec.vbase + (unsigned)rk);
-    }
-    // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
-    {
-        int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
-        const long long shift = p.vglobal0 - (long long)p.vlocal0;
-        for (int k = 0; k < nent; k++) out[k] = (int)(vid[row[k]] + shift);
-    }
-    // ---- vertices this cell creates, in creation order
-    unsigned seen = 0;
-    int created = 0;
-    for (int k = 0; k < nent; k++) {
-        const int e = row[k];
-        const unsigned bit = 1u << e;
-        if (!(owned & bit) || (seen & bit)) continue;
-        seen |= bit;
-        const long long slot = (long long)(rec.vbase - p.vlocal0) + created;
-        created++;
-        McF3 pos, col, nsum = {0.f, 0.f, 0.f};
+        // ---- vertices this cell creates; slot = vbase + rank in creation order
         const double stp = (double)g.step;
         const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;       // Cell.x/y/z are voxel coordinates
-        if (e == 12) {
-            // Cell.CalculateCenterVertex (Cell.cs:501-549)
-            double w[8];
+        for (unsigned todo = refd & owned; todo; todo &= todo - 1) {
+            const int e = __ffs(todo) - 1;
+            const long long slot = (long long)vid[e] - (long long)p.vlocal0;
+            McF3 pos, col, nsum = {0.f, 0.f, 0.f};
+            if (e == 12) {
+                // Cell.CalculateCenterVertex (Cell.cs:501-549)
+                double w[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) w[q] = 1.0 / (MC_EPS + fabs(v[q]));
-            double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
-            const double ox[8] = {0, 1, 1, 0, 0, 1, 1, 0}, oy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, oz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+                for (int q = 0; q < 8; q++) w[q] = 1.0 / (MC_EPS + fabs(v[q]));
+                double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+                McF3 fc = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int q = 0; q < 8; q++) { fx += ox[q] * w[q]; fy += oy[q] * w[q]; fz += oz[q] * w[q]; ff += w[q]; }
-            McF3 fc = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int cdx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, cdy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, cdz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-                const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx[q], cdy[q], cdz[q]) * 3;
-                const float wq = (float)w[q];
-                const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
-                if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
-                else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
-            }
-            pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
-            col.x = (float)(fc.x / ff); col.y = (float)(fc.y / ff); col.z = (float)(fc.z / ff);
-            double g12[3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                double s = w[0] * mc_vg(v, 0, a);
-#pragma unroll
-                for (int q = 1; q < 8; q++) s = s + w[q] * mc_vg(v, q, a);
-                g12[a] = s;
-            }
-            int times = 0;
-            for (int q = 0; q < nent; q++) times += (row[q] == 12);
-            const float gx = (float)g12[0], gy = (float)g12[1], gz = (float)g12[2];
-            for (int t = 0; t < times; t++) { nsum.x = nsum.x + gx; nsum.y = nsum.y + gy; nsum.z = nsum.z + gz; }
-        } else {
-            // Cell.AddFaceFromEdgeIndex, new-vertex branch (Cell.cs:313-357)
-            const int dx1 = d_lut[MCL_edgesrelx + e * 2], dx2 = d_lut[MCL_edgesrelx + e * 2 + 1];
-            const int dy1 = d_lut[MCL_edgesrely + e * 2], dy2 = d_lut[MCL_edgesrely + e * 2 + 1];
-            const int dz1 = d_lut[MCL_edgesrelz + e * 2], dz2 = d_lut[MCL_edgesrelz + e * 2 + 1];
-            const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};
-            const double w1 = 1.0 / (MC_EPS + fabs(v[ro[dz1 * 4 + dy1 * 2 + dx1]]));
-            const double w2 = 1.0 / (MC_EPS + fabs(v[ro[dz2 * 4 + dy2 * 2 + dx2]]));
-            double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
-            fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
-            fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
-            const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
-            const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
-            const float f1 = (float)w1, f2 = (float)w2;
-            const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
-            pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
-            col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
-            // gather the gradient contributions of every sharing cell in visiting order (normals[] accumulation
-            // order of the reference); the grid edge starts at lattice point (X, Y, Z) and runs along `axis`
-            const int X = i + min(dx1, dx2), Y = j + min(dy1, dy2), Z = kg + min(dz1, dz2);
-            const int axis = (dx1 != dx2) ? 0 : ((dy1 != dy2) ? 1 : 2);
-            // sharing cells (di, dj, dk relative to (X,Y,Z)) and the edge's local id there, in (k, j, i) order
-            const signed char share[3][4][4] = {
-                {{0, -1, -1, 6}, {0, 0, -1, 4}, {0, -1, 0, 2}, {0, 0, 0, 0}},
-                {{-1, 0, -1, 5}, {0, 0, -1, 7}, {-1, 0, 0, 1}, {0, 0, 0, 3}},
-                {{-1, -1, 0, 10}, {0, -1, 0, 11}, {-1, 0, 0, 9}, {0, 0, 0, 8}}};
-            for (int s = 0; s < 4; s++) {
-                const int ci = X + share[axis][s][0], cj = Y + share[axis][s][1], ck = Z + share[axis][s][2];
-                const int es = share[axis][s][3];
-                if (ci < 0 || cj < 0 || ck < 0 || ci >= g.ncx || cj >= g.ncy || ck >= g.ncz) continue;
-                const int ckl = ck - g.k0;
-                if (ckl < 0 || ckl >= g.nk) { atomicExch(p.error_flag, 3); continue; }
-                const signed char* srow;
-                int snent;
-                double sv[8];
-                if (ci == i && cj == j && ck == kg) {
-                    srow = row; snent = nent;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) sv[q] = v[q];
-                } else {
-                    const int sr = mc_find_record(p, ci, cj, ckl);
-                    if (sr < 0) { atomicExch(p.error_flag, 4); continue; }
-                    const unsigned sinfo = p.recs[sr].info;
-                    srow = d_lut + MC_LEAF_OFF(sinfo);
-                    snent = 3 * (int)MC_LEAF_NT(sinfo);
-                    mc_load_cell(g, p.dist, ci, cj, ck, sv);
+                for (int q = 0; q < 8; q++) {
+                    const int cdx = (0x66 >> q) & 1, cdy = (0xCC >> q) & 1, cdz = (0xF0 >> q) & 1;   // corner q -> (dx,dy,dz)
+                    fx += (double)cdx * w[q]; fy += (double)cdy * w[q]; fz += (double)cdz * w[q]; ff += w[q];
+                    const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx, cdy, cdz) * 3;
+                    const float wq = (float)w[q];
+                    const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
+                    if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
+                    else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
                 }
-                int times = 0;
-                for (int q = 0; q < snent; q++) times += (srow[q] == es);
-                if (times) mc_add_edge_gradients(sv, es, times, nsum);
+                pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
+                col.x = (float)(fc.x / ff); col.y = (float)(fc.y / ff); col.z = (float)(fc.z / ff);
+                float gr[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    double s = w[0] * mc_vg(v, 0, a);
+#pragma unroll
+                    for (int q = 1; q < 8; q++) s = s + w[q] * mc_vg(v, q, a);
+                    gr[a] = (float)s;
+                }
+                const int times = meta->occ[12];
+                for (int t = 0; t < times; t++) { nsum.x = nsum.x + gr[0]; nsum.y = nsum.y + gr[1]; nsum.z = nsum.z + gr[2]; }
+            } else {
+                // Cell.AddFaceFromEdgeIndex, new-vertex branch (Cell.cs:313-357)
+                int i1, i2;
+                mc_edge_ends(e, i1, i2);
+                const int dx1 = i1 & 1, dy1 = (i1 >> 1) & 1, dz1 = i1 >> 2, dx2 = i2 & 1, dy2 = (i2 >> 1) & 1, dz2 = i2 >> 2;
+                const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+                const double w1 = 1.0 / (MC_EPS + fabs(v[ro[i1]]));
+                const double w2 = 1.0 / (MC_EPS + fabs(v[ro[i2]]));
+                double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+                fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
+                fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
+                const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
+                const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
+                const float f1 = (float)w1, f2 = (float)w2;
+                const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
+                pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
+                col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
+                // gather the gradient contributions of every sharing cell in visiting order (normals[] accumulation
+                // order of the reference); the grid edge starts at lattice point (X, Y, Z) and runs along `axis`
+                const int X = i + min(dx1, dx2), Y = j + min(dy1, dy2), Z = kg + min(dz1, dz2);
+                const int axis = (dx1 != dx2) ? 0 : ((dy1 != dy2) ? 1 : 2);
+                // sharing cells (di, dj, dk relative to (X,Y,Z)) and the edge's local id there, in (k, j, i) order:
+                // 2 bits per offset (0 -> 0, 1 -> -1), 4 bits edge id, packed per (axis, s)
+#define SH(di, dj, dk, e) ((unsigned)(di) | (unsigned)(dj) << 1 | (unsigned)(dk) << 2 | (unsigned)(e) << 3)
+                const unsigned char share[3][4] = {
+                    {SH(0, 1, 1, 6), SH(0, 0, 1, 4), SH(0, 1, 0, 2), SH(0, 0, 0, 0)},
+                    {SH(1, 0, 1, 5), SH(0, 0, 1, 7), SH(1, 0, 0, 1), SH(0, 0, 0, 3)},
+                    {SH(1, 1, 0, 10), SH(0, 1, 0, 11), SH(1, 0, 0, 9), SH(0, 0, 0, 8)}};
+#undef SH
+                for (int s = 0; s < 4; s++) {
+                    const unsigned sh = share[axis][s];
+                    const int ci = X - (int)(sh & 1u), cj = Y - (int)((sh >> 1) & 1u), ck = Z - (int)((sh >> 2) & 1u);
+                    const int es = (int)(sh >> 3);
+                    if (ci < 0 || cj < 0 || ck < 0 || ci >= g.ncx || cj >= g.ncy || ck >= g.ncz) continue;
+                    const int ckl = ck - g.k0;
+                    if (ckl < 0 || ckl >= g.nk) { atomicExch(p.error_flag, 3); continue; }
+                    if (ci == i && cj == j && ck == kg) {
+                        mc_add_edge_gradients(v, es, meta->occ[es], nsum);
+                    } else {
+                        const int sr = mc_find_record(p, ci, cj, ckl);
+                        if (sr < 0) { atomicExch(p.error_flag, 4); continue; }
+                        const int times = d_meta[MC_LEAF_ROW(p.recs[sr].info)].occ[es];
+                        double sv[8];
+                        mc_load_cell(g, p.dist, ci, cj, ck, sv);
+                        mc_add_edge_gradients(sv, es, times, nsum);
+                    }
+                }
             }
+            mc_store_vertex(p, slot, pos, col, nsum, lo, hi);
         }
-        mc_store_vertex(p, slot, pos, col, nsum);
+    }
+    // AABB: warp min/max, then one atomic per warp and component
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const unsigned l = __reduce_min_sync(FULL, lo[a]), h = __reduce_max_sync(FULL, hi[a]);
+        if ((threadIdx.x & 31u) == 0) {
+            if (l != 0xFFFFFFFFu) atomicMin(p.aabb_keys + a, l);
+            if (h != 0u) atomicMax(p.aabb_keys + 3 + a, h);
+        }
     }
 }
 

@@ -23,7 +23,7 @@ struct McGrid {
 // One record per active cell, in the reference's visiting order (z outer, y, x inner).
 struct __align__(16) McRecord {
     unsigned cell;         // local linear cell id: i + ncx*(j + ncy*(k - k0))
-    unsigned info;         // leaf: row offset in the LUT blob [0:14) | ntris [14:18) | uses centre vertex [18]
+    unsigned info;         // leaf: tiling row id [0:10) | ntris [10:14) | uses centre vertex [14]
     unsigned vbase;        // exclusive prefix of created vertices (slab-local)
     unsigned tbase;        // exclusive prefix of triangles (slab-local)
 };
@@ -45,6 +45,7 @@ struct McEmitParams {
     const unsigned* counts;        // per chunk packed counts
     const uint4* base;             // per chunk exclusive prefix: x = records, y = verts, z = tris
     const McRecord* recs;
+    const uint4* masks;            // per active chunk: 128-bit activity mask (4 ballots)
     unsigned rec_begin, rec_end;   // records emitted by this slab (owned layers)
     unsigned vlocal0, tlocal0;     // slab-local prefix at the first owned layer
     long long vglobal0, tglobal0;  // global ids of the slab's first owned vertex / triangle
@@ -66,5 +67,5 @@ cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks
                            McTotals* totals, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
-                              McRecord* recs, cudaStream_t s);
+                              McRecord* recs, uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);
