@@ -39,6 +39,8 @@ struct McRowMeta {
     unsigned short refmask;      // slots (edges 0..11, centre 12) the row references
     unsigned short before[13];   // before[e] = slots first referenced earlier in the row than e
     unsigned char occ[13];       // how many times the row references slot e
+    unsigned char pad2[3];
+    unsigned long long occ_packed;   // occ[0..11], 3 bits each, pre-shifted into McRecord::aux position
 };
 
 static const signed char h_lut[MCL_BLOB_SIZE] = MCL_BLOB_INIT;
@@ -78,6 +80,10 @@ cudaError_t mc_init_tables()
                 m.occ[e]++;
             }
             m.refmask = (unsigned short)seen;
+            for (int e = 0; e < 12; e++) {
+                if (m.occ[e] > 7) return cudaErrorInvalidValue;
+                m.occ_packed |= (unsigned long long)m.occ[e] << (16 + 3 * e);
+            }
         }
     }
     if (rid != MCR_NROWS) return cudaErrorInvalidValue;
@@ -295,14 +301,6 @@ __device__ static inline void mc_load_cell(const McGrid& g, const float* __restr
     v[7] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 1, 1)) - iso;
 }
 
-__device__ static inline int mc_index_of(const double* v)   // Cell.cs:219-229: strict > 0
-{
-    int idx = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        if (v[k] > 0.0) idx |= 1 << k;
-    return idx;
-}
 
 // leaf + created-vertex count of an active cell
 __device__ __noinline__ static unsigned mc_resolve_cell(const McGrid& g, const float* __restrict__ dist, int idx, int i, int j, int kg)
@@ -672,6 +670,11 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
                     r.info = leaf[c];
                     r.vbase = b.y + MC_CNT_V(run);
                     r.tbase = b.z + MC_CNT_T(run);
+                    const McRowMeta* mt = d_meta + MC_LEAF_ROW(leaf[c]);
+                    const unsigned own = mc_owned_mask(i0 + c, j, kg) & mt->refmask;
+                    r.aux = mt->occ_packed | (unsigned long long)(__popc(mt->before[5] & own) | (__popc(mt->before[6] & own) << 4) |
+                                                                   (__popc(mt->before[10] & own) << 8) | (__popc(mt->before[12] & own) << 12));
+                    r.pad = 0;
                     recs[b.x + MC_CNT_ACT(run)] = r;
                     run += cnt[c];
                 }
@@ -697,8 +700,11 @@ cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4b mc_emit: one thread per active cell
+// K4b mc_emit: one thread per active cell.  Everything is unrolled over the edge id so that corner / gradient
+// selections are static (registers, no local memory) and a warp whose cells have similar cube indices walks
+// the same code; the only dynamically indexed table, the cell's 13 vertex ids, lives in shared memory.
 // ---------------------------------------------------------------------------------------------------
+#define MC_EMIT_THREADS 128
 
 // index of the record of cell (i, j, kl), -1 if that cell is not active
 __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j, int kl)
@@ -706,11 +712,11 @@ __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j,
     const McGrid& g = p.g;
     const unsigned chunk = ((unsigned)kl * (unsigned)g.ncy + (unsigned)j) * (unsigned)g.cpr + ((unsigned)i >> 7);
     const uint4 b = __ldg(p.base + chunk);
+    const uint4 m = __ldg(p.masks + chunk);       // garbage for inactive chunks: only used when the count says active
     if (MC_CNT_ACT(b.w) == 0u) return -1;
-    const uint4 m = __ldg(p.masks + chunk);
     const unsigned l = ((unsigned)i & 127u) >> 2, c = (unsigned)i & 3u;
-    const unsigned w[4] = {m.x, m.y, m.z, m.w};
-    if (!((w[c] >> l) & 1u)) return -1;
+    const unsigned wc = c == 0 ? m.x : (c == 1 ? m.y : (c == 2 ? m.z : m.w));
+    if (!((wc >> l) & 1u)) return -1;
     const unsigned below = (1u << l) - 1u;
     unsigned rank = __popc(m.x & below) + __popc(m.y & below) + __popc(m.z & below) + __popc(m.w & below);
     if (c > 0) rank += (m.x >> l) & 1u;
@@ -719,47 +725,39 @@ __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j,
     return (int)(b.x + rank);
 }
 
-// gradient row `r` (ORIGINAL corner numbering, Cell.cs:491-498), component a: v[p] - v[q]
-__device__ static inline double mc_vg(const double* v, int r, int a)
-{
-    // 8 rows x 3 components, (p,q) packed 3 bits each
-    const unsigned short tab[24] = {
-        0 | 1 << 3, 0 | 3 << 3, 0 | 4 << 3,    // corner 0
-        0 | 1 << 3, 1 | 2 << 3, 1 | 5 << 3,    // corner 1
-        3 | 2 << 3, 1 | 2 << 3, 2 | 6 << 3,    // corner 2
-        3 | 2 << 3, 0 | 3 << 3, 3 | 7 << 3,    // corner 3
-        4 | 5 << 3, 4 | 7 << 3, 0 | 4 << 3,    // corner 4
-        4 | 5 << 3, 5 | 6 << 3, 1 | 5 << 3,    // corner 5
-        7 | 6 << 3, 5 | 6 << 3, 2 | 6 << 3,    // corner 6
-        7 | 6 << 3, 4 | 7 << 3, 3 | 7 << 3};   // corner 7
-    const unsigned t = tab[r * 3 + a];
-    return v[t & 7u] - v[(t >> 3) & 7u];
-}
-
 struct McF3 { float x, y, z; };
 
-// end corners of edge e as positional indices dz*4 + dy*2 + dx (Luts.cs:26-28, Cell.cs:303-308)
-__device__ static inline void mc_edge_ends(int e, int& i1, int& i2)
+// gradient row R (ORIGINAL corner numbering, Cell.cs:491-498): component differences v[p] - v[q]
+template <int R>
+__device__ static inline void mc_vg_row(const double* v, double& gx, double& gy, double& gz)
 {
-    // (dx,dy,dz) pairs of EDGETORELATIVEPOS{X,Y,Z}: packed i1 | i2 << 3
-    const unsigned char tab[12] = {0 | 1 << 3, 1 | 3 << 3, 3 | 2 << 3, 2 | 0 << 3, 4 | 5 << 3, 5 | 7 << 3,
-                                   7 | 6 << 3, 6 | 4 << 3, 0 | 4 << 3, 1 | 5 << 3, 3 | 7 << 3, 2 | 6 << 3};
-    i1 = tab[e] & 7;
-    i2 = tab[e] >> 3;
+    constexpr int PX[8] = {0, 0, 3, 3, 4, 4, 7, 7}, QX[8] = {1, 1, 2, 2, 5, 5, 6, 6};
+    constexpr int PY[8] = {0, 1, 1, 0, 4, 5, 5, 4}, QY[8] = {3, 2, 2, 3, 7, 6, 6, 7};
+    constexpr int PZ[8] = {0, 1, 2, 3, 0, 1, 2, 3}, QZ[8] = {4, 5, 6, 7, 4, 5, 6, 7};
+    gx = v[PX[R]] - v[QX[R]];
+    gy = v[PY[R]] - v[QY[R]];
+    gz = v[PZ[R]] - v[QZ[R]];
 }
 
-// adds, for `times` references of local edge e in a sharing cell, the two end-corner gradient contributions
+// end corners of edge E as positional indices dz*4 + dy*2 + dx (Luts.cs:26-28, Cell.cs:303-308)
+__host__ __device__ constexpr int mc_end1(int e) { return e == 0 ? 0 : e == 1 ? 1 : e == 2 ? 3 : e == 3 ? 2 : e == 4 ? 4 : e == 5 ? 5 : e == 6 ? 7 : e == 7 ? 6 : e == 8 ? 0 : e == 9 ? 1 : e == 10 ? 3 : 2; }
+__host__ __device__ constexpr int mc_end2(int e) { return e == 0 ? 1 : e == 1 ? 3 : e == 2 ? 2 : e == 3 ? 0 : e == 4 ? 5 : e == 5 ? 7 : e == 6 ? 6 : e == 7 ? 4 : e == 8 ? 4 : e == 9 ? 5 : e == 10 ? 7 : 6; }
+__host__ __device__ constexpr int mc_reorder(int i) { return i == 2 ? 3 : i == 3 ? 2 : i == 6 ? 7 : i == 7 ? 6 : i; }   // vv[] (Cell.cs:453-460)
+
+// adds, for `times` references of local edge E in a sharing cell, the two end-corner gradient contributions
 // exactly like Cell.AddGradientFromIndex (Cell.cs:154-158,331-333): note vg is indexed with the dz*4+dy*2+dx
 // corner index although its rows are in the v0..v7 numbering -- a quirk of the reference that is preserved.
-__device__ static inline void mc_add_edge_gradients(const double* v, int e, int times, McF3& n)
+template <int E>
+__device__ static inline void mc_add_edge_gradients(const double* v, int times, McF3& n)
 {
-    int i1, i2;
-    mc_edge_ends(e, i1, i2);
-    const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};                     // vv[] re-ordering (Cell.cs:453-460)
-    const double w1 = 1.0 / (MC_EPS + fabs(v[ro[i1]]));
-    const double w2 = 1.0 / (MC_EPS + fabs(v[ro[i2]]));
-    const float g1x = (float)(mc_vg(v, i1, 0) * w1), g1y = (float)(mc_vg(v, i1, 1) * w1), g1z = (float)(mc_vg(v, i1, 2) * w1);
-    const float g2x = (float)(mc_vg(v, i2, 0) * w2), g2y = (float)(mc_vg(v, i2, 1) * w2), g2z = (float)(mc_vg(v, i2, 2) * w2);
+    constexpr int I1 = mc_end1(E), I2 = mc_end2(E);
+    const double w1 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I1)]));
+    const double w2 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I2)]));
+    double ax, ay, az, bx, by, bz;
+    mc_vg_row<I1>(v, ax, ay, az);
+    mc_vg_row<I2>(v, bx, by, bz);
+    const float g1x = (float)(ax * w1), g1y = (float)(ay * w1), g1z = (float)(az * w1);
+    const float g2x = (float)(bx * w2), g2y = (float)(by * w2), g2z = (float)(bz * w2);
     for (int t = 0; t < times; t++) {
         n.x = n.x + g1x; n.y = n.y + g1y; n.z = n.z + g1z;
         n.x = n.x + g2x; n.y = n.y + g2y; n.z = n.z + g2z;
@@ -799,9 +797,157 @@ __device__ static inline void mc_store_vertex(const McEmitParams& p, long long s
     hi[0] = max(hi[0], mc_float_key(pos.x)); hi[1] = max(hi[1], mc_float_key(pos.y)); hi[2] = max(hi[2], mc_float_key(pos.z));
 }
 
-__global__ void __launch_bounds__(128)
+// who creates the vertex on edge E of cell (i, j, kg) when the cell itself does not: offset of the creating cell
+// (the sharing cell smallest in (k, j, i)) and the edge's id there
+template <int E>
+__device__ static inline void mc_creator_of(int i, int j, int kg, int& di, int& dj, int& dk, int& e2)
+{
+    di = dj = dk = 0;
+    e2 = E;
+    if (E == 0) { dk = kg > 0 ? -1 : 0; dj = j > 0 ? -1 : 0; e2 = dk ? (dj ? 6 : 4) : (dj ? 2 : 0); }
+    else if (E == 1) { dk = -1; e2 = 5; }
+    else if (E == 2) { dk = -1; e2 = 6; }
+    else if (E == 3) { dk = kg > 0 ? -1 : 0; di = i > 0 ? -1 : 0; e2 = dk ? (di ? 5 : 7) : (di ? 1 : 3); }
+    else if (E == 4) { dj = -1; e2 = 6; }
+    else if (E == 7) { di = -1; e2 = 5; }
+    else if (E == 8) { if (j > 0) { dj = -1; if (i > 0) { di = -1; e2 = 10; } else e2 = 11; } else { di = -1; e2 = 9; } }
+    else if (E == 9) { dj = -1; e2 = 10; }
+    else if (E == 11) { di = -1; e2 = 10; }
+}
+
+// vertex id (slab-local) of slot E referenced by this cell
+template <int E>
+__device__ static inline int mc_vertex_id(const McEmitParams& p, const McRecord& rec, const McRowMeta* meta, unsigned owned,
+                                          int i, int j, int kl, int kg)
+{
+    if ((owned >> E) & 1u) return (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[E] & owned));
+    int di, dj, dk, e2;
+    mc_creator_of<E>(i, j, kg, di, dj, dk, e2);
+    const int oi = i + di, oj = j + dj, okl = kl + dk;
+    const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl) : -1;
+    if (orr < 0) { atomicExch(p.error_flag, 1); return 0; }
+    const McRecord* orp = p.recs + orr;
+    const uint4 oa = __ldg(reinterpret_cast<const uint4*>(orp));            // cell, info, vbase, tbase
+    const unsigned long long aux = __ldg(&orp->aux);
+    if (e2 == 5) return (int)(oa.z + MC_AUX_RANK(aux, 0));
+    if (e2 == 6) return (int)(oa.z + MC_AUX_RANK(aux, 1));
+    if (e2 == 10) return (int)(oa.z + MC_AUX_RANK(aux, 2));
+    // creator on the grid boundary (i, j or k == 0): it also creates edges other than 5, 6, 10
+    const McRowMeta* om = d_meta + MC_LEAF_ROW(oa.y);
+    if (!((om->refmask >> e2) & 1u)) { atomicExch(p.error_flag, 2); return 0; }
+    return (int)(oa.z + (unsigned)__popc((unsigned)om->before[e2] & mc_owned_mask(oi, oj, kg + dk) & om->refmask));
+}
+
+// contribution of one sharing cell (ci, cj, ck), which sees the grid edge as its local edge ES, to a vertex normal
+template <int ES>
+__device__ static inline void mc_gather_from(const McEmitParams& p, int ci, int cj, int ck, McF3& nsum)
+{
+    const McGrid& g = p.g;
+    if (ci < 0 || cj < 0 || ck < 0 || ci >= g.ncx || cj >= g.ncy || ck >= g.ncz) return;
+    const int ckl = ck - g.k0;
+    if (ckl < 0 || ckl >= g.nk) { atomicExch(p.error_flag, 3); return; }
+    const int sr = mc_find_record(p, ci, cj, ckl);
+    if (sr < 0) { atomicExch(p.error_flag, 4); return; }
+    const int times = (int)MC_AUX_OCC(__ldg(&p.recs[sr].aux), ES);
+    double sv[8];
+    mc_load_cell(g, p.dist, ci, cj, ck, sv);
+    mc_add_edge_gradients<ES>(sv, times, nsum);
+}
+
+// position + colour of the vertex the cell creates on its edge E (Cell.AddFaceFromEdgeIndex, new-vertex branch,
+// Cell.cs:313-357), then the gradient contributions of every sharing cell in visiting order (the accumulation order
+// of the reference's normals[]): the grid edge starts at lattice point (X, Y, Z) and runs along AXIS; sharing cells
+// in (k, j, i) order are  x: (Y-1,Z-1) e6, (Y,Z-1) e4, (Y-1,Z) e2, (Y,Z) e0;  y: (X-1,Z-1) e5, (X,Z-1) e7, (X-1,Z) e1,
+// (X,Z) e3;  z: (X-1,Y-1) e10, (X,Y-1) e11, (X-1,Y) e9, (X,Y) e8.
+template <int E>
+__device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const double* v, int occ_self, int i, int j, int kg,
+                                                    long long slot, unsigned* lo, unsigned* hi)
+{
+    const McGrid& g = p.g;
+    constexpr int I1 = mc_end1(E), I2 = mc_end2(E);
+    constexpr int dx1 = I1 & 1, dy1 = (I1 >> 1) & 1, dz1 = I1 >> 2, dx2 = I2 & 1, dy2 = (I2 >> 1) & 1, dz2 = I2 >> 2;
+    const double stp = (double)g.step;
+    const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;           // Cell.x/y/z are voxel coordinates
+    const double w1 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I1)]));
+    const double w2 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I2)]));
+    double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+    fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
+    fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
+    const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
+    const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
+    const float f1 = (float)w1, f2 = (float)w2;
+    const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
+    McF3 pos, col, nsum = {0.f, 0.f, 0.f};
+    pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
+    col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
+    constexpr int AXIS = (dx1 != dx2) ? 0 : ((dy1 != dy2) ? 1 : 2);
+    const int X = i + (dx1 < dx2 ? dx1 : dx2), Y = j + (dy1 < dy2 ? dy1 : dy2), Z = kg + (dz1 < dz2 ? dz1 : dz2);
+    // the creating cell is the first sharing cell in visiting order; it sees the edge as E
+    mc_add_edge_gradients<E>(v, occ_self, nsum);
+    if (AXIS == 0) {          // this cell is one of (X, Y-1|Y, Z-1|Z); skip itself, keep the order
+        if (E == 6) { mc_gather_from<4>(p, X, Y, Z - 1, nsum); mc_gather_from<2>(p, X, Y - 1, Z, nsum); mc_gather_from<0>(p, X, Y, Z, nsum); }
+        if (E == 4) { mc_gather_from<2>(p, X, Y - 1, Z, nsum); mc_gather_from<0>(p, X, Y, Z, nsum); }
+        if (E == 2) { mc_gather_from<0>(p, X, Y, Z, nsum); }
+    } else if (AXIS == 1) {
+        if (E == 5) { mc_gather_from<7>(p, X, Y, Z - 1, nsum); mc_gather_from<1>(p, X - 1, Y, Z, nsum); mc_gather_from<3>(p, X, Y, Z, nsum); }
+        if (E == 7) { mc_gather_from<1>(p, X - 1, Y, Z, nsum); mc_gather_from<3>(p, X, Y, Z, nsum); }
+        if (E == 1) { mc_gather_from<3>(p, X, Y, Z, nsum); }
+    } else {
+        if (E == 10) { mc_gather_from<11>(p, X, Y - 1, Z, nsum); mc_gather_from<9>(p, X - 1, Y, Z, nsum); mc_gather_from<8>(p, X, Y, Z, nsum); }
+        if (E == 11) { mc_gather_from<9>(p, X - 1, Y, Z, nsum); mc_gather_from<8>(p, X, Y, Z, nsum); }
+        if (E == 9) { mc_gather_from<8>(p, X, Y, Z, nsum); }
+    }
+    mc_store_vertex(p, slot, pos, col, nsum, lo, hi);
+}
+
+// Cell.CalculateCenterVertex (Cell.cs:501-549) + its accumulated gradient
+__device__ static inline void mc_create_center_vertex(const McEmitParams& p, const double* v, int times, int i, int j, int kg,
+                                                      long long slot, unsigned* lo, unsigned* hi)
+{
+    const McGrid& g = p.g;
+    const double stp = (double)g.step;
+    const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;
+    double w[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) w[q] = 1.0 / (MC_EPS + fabs(v[q]));
+    double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+    McF3 fc = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int cdx = (0x66 >> q) & 1, cdy = (0xCC >> q) & 1, cdz = (0xF0 >> q) & 1;   // corner q -> (dx,dy,dz)
+        fx += (double)cdx * w[q]; fy += (double)cdy * w[q]; fz += (double)cdz * w[q]; ff += w[q];
+        const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx, cdy, cdz) * 3;
+        const float wq = (float)w[q];
+        const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
+        if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
+        else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
+    }
+    McF3 pos, col, nsum = {0.f, 0.f, 0.f};
+    pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
+    col.x = (float)(fc.x / ff); col.y = (float)(fc.y / ff); col.z = (float)(fc.z / ff);
+    double gs[3] = {0.0, 0.0, 0.0};
+    {
+        double gx, gy, gz;
+        mc_vg_row<0>(v, gx, gy, gz); gs[0] = w[0] * gx; gs[1] = w[0] * gy; gs[2] = w[0] * gz;
+        mc_vg_row<1>(v, gx, gy, gz); gs[0] = gs[0] + w[1] * gx; gs[1] = gs[1] + w[1] * gy; gs[2] = gs[2] + w[1] * gz;
+        mc_vg_row<2>(v, gx, gy, gz); gs[0] = gs[0] + w[2] * gx; gs[1] = gs[1] + w[2] * gy; gs[2] = gs[2] + w[2] * gz;
+        mc_vg_row<3>(v, gx, gy, gz); gs[0] = gs[0] + w[3] * gx; gs[1] = gs[1] + w[3] * gy; gs[2] = gs[2] + w[3] * gz;
+        mc_vg_row<4>(v, gx, gy, gz); gs[0] = gs[0] + w[4] * gx; gs[1] = gs[1] + w[4] * gy; gs[2] = gs[2] + w[4] * gz;
+        mc_vg_row<5>(v, gx, gy, gz); gs[0] = gs[0] + w[5] * gx; gs[1] = gs[1] + w[5] * gy; gs[2] = gs[2] + w[5] * gz;
+        mc_vg_row<6>(v, gx, gy, gz); gs[0] = gs[0] + w[6] * gx; gs[1] = gs[1] + w[6] * gy; gs[2] = gs[2] + w[6] * gz;
+        mc_vg_row<7>(v, gx, gy, gz); gs[0] = gs[0] + w[7] * gx; gs[1] = gs[1] + w[7] * gy; gs[2] = gs[2] + w[7] * gz;
+    }
+    const float gx = (float)gs[0], gy = (float)gs[1], gz = (float)gs[2];
+    for (int t = 0; t < times; t++) { nsum.x = nsum.x + gx; nsum.y = nsum.y + gy; nsum.z = nsum.z + gz; }
+    mc_store_vertex(p, slot, pos, col, nsum, lo, hi);
+}
+
+#define MC_FOR_EDGES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11)
+
+__global__ void __launch_bounds__(MC_EMIT_THREADS)
 mc_emit_kernel(const McEmitParams p)
 {
+    __shared__ int s_vid[MC_EMIT_THREADS][13];
     const McGrid& g = p.g;
     const unsigned r = p.rec_begin + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
@@ -817,131 +963,31 @@ mc_emit_kernel(const McEmitParams p)
         const int nent = 3 * (int)MC_LEAF_NT(rec.info);
         const unsigned owned = mc_owned_mask(i, j, kg);
         const unsigned refd = meta->refmask;
+        int* vid = s_vid[threadIdx.x];
 
         double v[8];
         mc_load_cell(g, p.dist, i, j, kg, v);
 
         // ---- vertex id of every slot this cell references
-        int vid[13];
-        for (unsigned todo = refd; todo; todo &= todo - 1) {
-            const int e = __ffs(todo) - 1;
-            if ((owned >> e) & 1u) {
-                vid[e] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[e] & owned));
-                continue;
-            }
-            // creator = sharing cell smallest in (k, j, i); e2 = the edge's id in the creator's numbering
-            int di = 0, dj = 0, dk = 0, e2 = e;
-            switch (e) {
-            case 0: dk = kg > 0 ? -1 : 0; dj = j > 0 ? -1 : 0; e2 = dk ? (dj ? 6 : 4) : (dj ? 2 : 0); break;
-            case 1: dk = -1; e2 = 5; break;
-            case 2: dk = -1; e2 = 6; break;
-            case 3: dk = kg > 0 ? -1 : 0; di = i > 0 ? -1 : 0; e2 = dk ? (di ? 5 : 7) : (di ? 1 : 3); break;
-            case 4: dj = -1; e2 = 6; break;
-            case 7: di = -1; e2 = 5; break;
-            case 8: if (j > 0) { dj = -1; if (i > 0) { di = -1; e2 = 10; } else e2 = 11; } else { di = -1; e2 = 9; } break;
-            case 9: dj = -1; e2 = 10; break;
-            case 11: di = -1; e2 = 10; break;
-            }
-            const int oi = i + di, oj = j + dj, okl = kl + dk;
-            const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl) : -1;
-            if (orr < 0) { atomicExch(p.error_flag, 1); vid[e] = 0; continue; }
-            const McRecord orec = p.recs[orr];
-            const McRowMeta* om = d_meta + MC_LEAF_ROW(orec.info);
-            if (!((om->refmask >> e2) & 1u)) { atomicExch(p.error_flag, 2); vid[e] = 0; continue; }
-            vid[e] = (int)(orec.vbase + (unsigned)__popc((unsigned)om->before[e2] & mc_owned_mask(oi, oj, kg + dk)));
-        }
+#define VID(E) if ((refd >> E) & 1u) vid[E] = mc_vertex_id<E>(p, rec, meta, owned, i, j, kl, kg);
+        MC_FOR_EDGES(VID)
+#undef VID
+        if ((refd >> 12) & 1u) vid[12] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[12] & owned));
         // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
         {
             int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
             const int shift = (int)(p.vglobal0 - (long long)p.vlocal0);
             for (int k = 0; k < nent; k++) out[k] = vid[row[k]] + shift;
         }
-        // ---- vertices this cell creates; slot = vbase + rank in creation order
-        const double stp = (double)g.step;
-        const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;       // Cell.x/y/z are voxel coordinates
-        for (unsigned todo = refd & owned; todo; todo &= todo - 1) {
-            const int e = __ffs(todo) - 1;
-            const long long slot = (long long)vid[e] - (long long)p.vlocal0;
-            McF3 pos, col, nsum = {0.f, 0.f, 0.f};
-            if (e == 12) {
-                // Cell.CalculateCenterVertex (Cell.cs:501-549)
-                double w[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) w[q] = 1.0 / (MC_EPS + fabs(v[q]));
-                double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
-                McF3 fc = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int cdx = (0x66 >> q) & 1, cdy = (0xCC >> q) & 1, cdz = (0xF0 >> q) & 1;   // corner q -> (dx,dy,dz)
-                    fx += (double)cdx * w[q]; fy += (double)cdy * w[q]; fz += (double)cdz * w[q]; ff += w[q];
-                    const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx, cdy, cdz) * 3;
-                    const float wq = (float)w[q];
-                    const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
-                    if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
-                    else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
-                }
-                pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
-                col.x = (float)(fc.x / ff); col.y = (float)(fc.y / ff); col.z = (float)(fc.z / ff);
-                float gr[3];
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    double s = w[0] * mc_vg(v, 0, a);
-#pragma unroll
-                    for (int q = 1; q < 8; q++) s = s + w[q] * mc_vg(v, q, a);
-                    gr[a] = (float)s;
-                }
-                const int times = meta->occ[12];
-                for (int t = 0; t < times; t++) { nsum.x = nsum.x + gr[0]; nsum.y = nsum.y + gr[1]; nsum.z = nsum.z + gr[2]; }
-            } else {
-                // Cell.AddFaceFromEdgeIndex, new-vertex branch (Cell.cs:313-357)
-                int i1, i2;
-                mc_edge_ends(e, i1, i2);
-                const int dx1 = i1 & 1, dy1 = (i1 >> 1) & 1, dz1 = i1 >> 2, dx2 = i2 & 1, dy2 = (i2 >> 1) & 1, dz2 = i2 >> 2;
-                const int ro[8] = {0, 1, 3, 2, 4, 5, 7, 6};
-                const double w1 = 1.0 / (MC_EPS + fabs(v[ro[i1]]));
-                const double w2 = 1.0 / (MC_EPS + fabs(v[ro[i2]]));
-                double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
-                fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
-                fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
-                const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
-                const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
-                const float f1 = (float)w1, f2 = (float)w2;
-                const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
-                pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
-                col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
-                // gather the gradient contributions of every sharing cell in visiting order (normals[] accumulation
-                // order of the reference); the grid edge starts at lattice point (X, Y, Z) and runs along `axis`
-                const int X = i + min(dx1, dx2), Y = j + min(dy1, dy2), Z = kg + min(dz1, dz2);
-                const int axis = (dx1 != dx2) ? 0 : ((dy1 != dy2) ? 1 : 2);
-                // sharing cells (di, dj, dk relative to (X,Y,Z)) and the edge's local id there, in (k, j, i) order:
-                // 2 bits per offset (0 -> 0, 1 -> -1), 4 bits edge id, packed per (axis, s)
-#define SH(di, dj, dk, e) ((unsigned)(di) | (unsigned)(dj) << 1 | (unsigned)(dk) << 2 | (unsigned)(e) << 3)
-                const unsigned char share[3][4] = {
-                    {SH(0, 1, 1, 6), SH(0, 0, 1, 4), SH(0, 1, 0, 2), SH(0, 0, 0, 0)},
-                    {SH(1, 0, 1, 5), SH(0, 0, 1, 7), SH(1, 0, 0, 1), SH(0, 0, 0, 3)},
-                    {SH(1, 1, 0, 10), SH(0, 1, 0, 11), SH(1, 0, 0, 9), SH(0, 0, 0, 8)}};
-#undef SH
-                for (int s = 0; s < 4; s++) {
-                    const unsigned sh = share[axis][s];
-                    const int ci = X - (int)(sh & 1u), cj = Y - (int)((sh >> 1) & 1u), ck = Z - (int)((sh >> 2) & 1u);
-                    const int es = (int)(sh >> 3);
-                    if (ci < 0 || cj < 0 || ck < 0 || ci >= g.ncx || cj >= g.ncy || ck >= g.ncz) continue;
-                    const int ckl = ck - g.k0;
-                    if (ckl < 0 || ckl >= g.nk) { atomicExch(p.error_flag, 3); continue; }
-                    if (ci == i && cj == j && ck == kg) {
-                        mc_add_edge_gradients(v, es, meta->occ[es], nsum);
-                    } else {
-                        const int sr = mc_find_record(p, ci, cj, ckl);
-                        if (sr < 0) { atomicExch(p.error_flag, 4); continue; }
-                        const int times = d_meta[MC_LEAF_ROW(p.recs[sr].info)].occ[es];
-                        double sv[8];
-                        mc_load_cell(g, p.dist, ci, cj, ck, sv);
-                        mc_add_edge_gradients(sv, es, times, nsum);
-                    }
-                }
-            }
-            mc_store_vertex(p, slot, pos, col, nsum, lo, hi);
+        // ---- vertices this cell creates; slot = id - vlocal0
+        const unsigned mine = refd & owned;
+#define VERT(E) if ((mine >> E) & 1u) mc_create_edge_vertex<E>(p, v, (int)MC_AUX_OCC(rec.aux, E), i, j, kg, (long long)vid[E] - (long long)p.vlocal0, lo, hi);
+        VERT(5) VERT(6) VERT(10)
+        if (mine & 0x0B9Fu) {     // grid-boundary cells also create edges 0-4, 7-9, 11
+            VERT(0) VERT(1) VERT(2) VERT(3) VERT(4) VERT(7) VERT(8) VERT(9) VERT(11)
         }
+#undef VERT
+        if ((mine >> 12) & 1u) mc_create_center_vertex(p, v, meta->occ[12], i, j, kg, (long long)vid[12] - (long long)p.vlocal0, lo, hi);
     }
     // AABB: warp min/max, then one atomic per warp and component
 #pragma unroll
@@ -958,6 +1004,6 @@ cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
 {
     const unsigned n = p.rec_end - p.rec_begin;
     if (n == 0) return cudaSuccess;
-    mc_emit_kernel<<<(n + 127u) / 128u, 128, 0, s>>>(p);
+    mc_emit_kernel<<<(n + MC_EMIT_THREADS - 1u) / MC_EMIT_THREADS, MC_EMIT_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }

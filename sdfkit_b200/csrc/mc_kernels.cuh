@@ -21,12 +21,18 @@ struct McGrid {
 };
 
 // One record per active cell, in the reference's visiting order (z outer, y, x inner).
-struct __align__(16) McRecord {
+struct __align__(32) McRecord {
     unsigned cell;         // local linear cell id: i + ncx*(j + ncy*(k - k0))
     unsigned info;         // leaf: tiling row id [0:10) | ntris [10:14) | uses centre vertex [14]
     unsigned vbase;        // exclusive prefix of created vertices (slab-local)
     unsigned tbase;        // exclusive prefix of triangles (slab-local)
+    unsigned long long aux;   // what neighbours ask of this cell, so that a lookup is one 32-byte read:
+                              //   [0:16)  creation rank of slots 5, 6, 10, 12 (4 bits each) -> vertex id = vbase + rank
+                              //   [16:52) how often the row references edge e = 0..11 (3 bits each)
+    unsigned long long pad;
 };
+#define MC_AUX_RANK(aux, q) ((unsigned)((aux) >> (4 * (q))) & 0xFu)           /* q: 0 -> e5, 1 -> e6, 2 -> e10, 3 -> centre */
+#define MC_AUX_OCC(aux, e) ((unsigned)((aux) >> (16 + 3 * (e))) & 0x7u)
 
 // per-chunk packed counts: nactive [0:8) | nverts [8:19) | ntris [19:30)
 #define MC_CNT_ACT(c) ((c) & 0xFFu)
