@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- the SdfKit hot path on B200: SdfExpr.ToSdf() -> Voxels sampling -> MarchingCubes meshing.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n GRID] [--scene readme|csg50|sphere]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid N] [--scene readme|csg50|sphere]
 
 One "step" = one pass of the hot path over one grid of the README RepeatXY scene (BASELINE.json): sample every
 voxel (distance + colour, clip to bounds) into HBM, then mesh it (classify -> scan -> compact -> emit).  The SDF
@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 
 METRIC = "voxel_samples_per_s"
 UNIT = "voxels/s"
-WEAK_GRID = {1: 1024, 2: 1288, 4: 1624, 8: 2048}       # n^3 ~= N * 1024^3
+WEAK_GRID = {1: 1024, 2: 1280, 4: 1624, 8: 2048}       # n^3 ~= N * 1024^3 (1280 = 10 full 128-voxel chunks per row)
 
 
 def scene_by_name(name):
@@ -180,20 +180,28 @@ def run_ours(args):
         sampler.start()
     l0 = ctx.launch_count()
     sample_ms, stage = [], {"classify_ms": [], "scan_ms": [], "compact_ms": [], "emit_ms": []}
+    host = {"sample_classify": 0.0, "allgather": 0.0, "emit": 0.0}
     barrier()
     ctx.mark(0)
     w0 = time.perf_counter()
     for _ in range(args.steps):
+        h0 = time.perf_counter()
         ctx.mark(2)
         slab.sample()
         ctx.mark(3)
         nv, nt = slab.classify()
+        h1 = time.perf_counter()
         if world > 1:
             excl, tot = skd.all_gather_counts(nv, nt, device=dev)
             vb, tb = excl[rank]
         else:
             vb, tb, tot = 0, 0, (nv, nt)
+        h2 = time.perf_counter()
         slab.emit(vb, tb)
+        h3 = time.perf_counter()
+        host["sample_classify"] += (h1 - h0) * 1e3
+        host["allgather"] += (h2 - h1) * 1e3
+        host["emit"] += (h3 - h2) * 1e3
         sample_ms.append(ctx.elapsed(2, 3))
         st = slab.mesh.stats()
         for k in stage:
@@ -219,7 +227,20 @@ def run_ours(args):
     k1_ms = statistics.mean(sample_ms)
     achieved = 16.0 * slab_vox / (k1_ms * 1e-3) / 1e9
     mesh_ms = {k: statistics.mean(v) for k, v in stage.items()}
-    cells = (n - 1) * (n - 1) * (ke - kb)
+    cells = (n - 1) * (n - 1) * (n - 1)
+    # per-rank view of the step (device stage times + host-side wall per phase), gathered to rank 0
+    mine = [k1_ms] + [mesh_ms[k] for k in ("classify_ms", "scan_ms", "compact_ms", "emit_ms")] + [host[k] / args.steps for k in ("sample_classify", "allgather", "emit")]
+    per_rank = torch.tensor(mine, dtype=torch.float64, device=dev)
+    if world > 1:
+        allr = [torch.empty_like(per_rank) for _ in range(world)]
+        dist.all_gather(allr, per_rank)
+        per_rank = torch.stack(allr)
+    else:
+        per_rank = per_rank[None]
+    per_rank = per_rank.cpu().numpy()
+    names = ["sample_ms", "classify_ms", "scan_ms", "compact_ms", "emit_ms", "host_sample_classify_ms", "host_allgather_ms", "host_emit_ms"]
+    rank_stages = {nm: [round(float(x), 4) for x in per_rank[:, i]] for i, nm in enumerate(names)}
+    mesh_total_ms = float(per_rank[:, 1:5].sum(axis=1).max())
 
     # ---- e2e through the public API: Sdf.ToMesh(min, max, n, n, n) -> Mesh in host memory, every step
     e2e = None
@@ -285,9 +306,10 @@ def run_ours(args):
                        "parity_mode": "IEEE f32/f64, no FMA contraction (bit-exact vs the CPU oracle)"},
             "tris_per_s": ntris_total / (ms_per_step * 1e-3), "triangles": ntris_total, "vertices": int(tot[0]),
             "stages_ms": dict(sample_ms=k1_ms, **mesh_ms),
-            "mesh": {"tris_per_s": ntris_total / world / (sum(mesh_ms.values()) * 1e-3) * world,
-                     "cells_per_s": cells / (sum(mesh_ms.values()) * 1e-3) * world,
-                     "classify_gbs": 4.0 * n * n * (slab.z1 - slab.z0) / (mesh_ms["classify_ms"] * 1e-3) / 1e9},
+            "mesh": {"tris_per_s": ntris_total / (mesh_total_ms * 1e-3), "cells_per_s": cells / (mesh_total_ms * 1e-3),
+                     "classify_gbs_rank0": 4.0 * n * n * (slab.z1 - slab.z0) / (mesh_ms["classify_ms"] * 1e-3) / 1e9,
+                     "note": "meshing stages only (K2-K4), slowest rank"},
+            "per_rank_ms": rank_stages,
             "roofline": {"kernel": "sdfk_k_sample", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 16.0 * slab_vox, "launch_ms": k1_ms},
@@ -307,7 +329,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="grid size override (default: 1024 per GPU-equivalent)")
+    ap.add_argument("--grid", dest="n", type=int, default=0, help="grid size override (default: 1024 per GPU-equivalent)")
     ap.add_argument("--scene", default="readme")
     ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")

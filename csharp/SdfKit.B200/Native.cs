@@ -1,0 +1,71 @@
+// Native.cs -- P/Invoke declarations for libsdfk.so (include/sdfk.h).  SOURCE ONLY: this image has no .NET
+// toolchain, so this shim is not compiled or tested here; the Python mirror (sdfkit_b200/) exercises the same ABI.
+using System;
+using System.Runtime.InteropServices;
+
+namespace SdfKit.B200
+{
+    internal static unsafe class Native
+    {
+        const string Lib = "sdfk";   // libsdfk.so
+
+        [UnmanagedFunctionPointer(CallingConvention.Cdecl)]
+        public delegate void ProgressFn(float fraction, IntPtr user);
+
+        [DllImport(Lib)] public static extern IntPtr sdfk_last_error();
+        [DllImport(Lib)] public static extern int sdfk_version();
+
+        [DllImport(Lib)] public static extern int sdfk_ctx_create(int device, out IntPtr ctx);
+        [DllImport(Lib)] public static extern int sdfk_ctx_destroy(IntPtr ctx);
+        [DllImport(Lib)] public static extern int sdfk_ctx_synchronize(IntPtr ctx);
+
+        [DllImport(Lib)] public static extern int sdfk_sdf_compile(IntPtr ctx, byte[] body, UIntPtr len, out IntPtr sdf);
+        [DllImport(Lib)] public static extern int sdfk_sdf_destroy(IntPtr sdf);
+        [DllImport(Lib)] public static extern int sdfk_sdf_eval(IntPtr sdf, float* xyz, float* rgbd, long n);
+
+        [DllImport(Lib)] public static extern int sdfk_voxels_sample(IntPtr ctx, IntPtr sdf, float* min, float* max,
+            int nx, int ny, int nz, int clip, out IntPtr voxels);
+        [DllImport(Lib)] public static extern int sdfk_voxels_import(IntPtr ctx, float* values, float* colors, float* min, float* max,
+            int nx, int ny, int nz, out IntPtr voxels);
+        [DllImport(Lib)] public static extern int sdfk_voxels_export(IntPtr voxels, float* values, float* colors);
+        [DllImport(Lib)] public static extern int sdfk_voxels_clip(IntPtr voxels);
+        [DllImport(Lib)] public static extern int sdfk_voxels_destroy(IntPtr voxels);
+
+        [DllImport(Lib)] public static extern int sdfk_mesh_create(IntPtr ctx, IntPtr voxels, float iso, int step,
+            float* transform, float* normalTransform, ProgressFn? progress, IntPtr user, out IntPtr mesh);
+        [DllImport(Lib)] public static extern int sdfk_mesh_counts(IntPtr mesh, out long nverts, out long ntris);
+        [DllImport(Lib)] public static extern int sdfk_mesh_export(IntPtr mesh, float* vertices, float* colors, float* normals,
+            int* triangles, float* aabb);
+        [DllImport(Lib)] public static extern int sdfk_mesh_destroy(IntPtr mesh);
+
+        [DllImport(Lib)] public static extern int sdfk_render(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos, float* invViewProj,
+            float near, float far, int iterations, int rowBegin, int rowEnd, float* rgb);
+        [DllImport(Lib)] public static extern int sdfk_render_depth(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos,
+            float* invViewProj, float near, int iterations, int rowBegin, int rowEnd, float* depth);
+
+        public static void Check(int status)
+        {
+            if (status == 0) return;
+            var msg = Marshal.PtrToStringUTF8(sdfk_last_error()) ?? "unknown error";
+            if (status == -4) throw new NotSupportedException(msg);
+            throw new InvalidOperationException($"libsdfk error {status}: {msg}");
+        }
+    }
+
+    /// <summary>One GPU + one stream; shared by every GpuSdf of the process.</summary>
+    public sealed class GpuContext : SafeHandle
+    {
+        static readonly Lazy<GpuContext> shared = new(() => new GpuContext(
+            int.TryParse(Environment.GetEnvironmentVariable("LOCAL_RANK"), out var r) ? r : 0));
+        public static GpuContext Shared => shared.Value;
+
+        public GpuContext(int device) : base(IntPtr.Zero, true)
+        {
+            Native.Check(Native.sdfk_ctx_create(device, out var h));
+            SetHandle(h);
+        }
+        public override bool IsInvalid => handle == IntPtr.Zero;
+        protected override bool ReleaseHandle() => Native.sdfk_ctx_destroy(handle) == 0;
+        internal IntPtr Ptr => handle;
+    }
+}
