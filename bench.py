@@ -306,7 +306,7 @@ def run_ours(args):
                        "parity_mode": "IEEE f32/f64, no FMA contraction (bit-exact vs the CPU oracle)"},
             "tris_per_s": ntris_total / (ms_per_step * 1e-3), "triangles": ntris_total, "vertices": int(tot[0]),
             "stages_ms": dict(sample_ms=k1_ms, **mesh_ms),
-            "mesh": {"tris_per_s": ntris_total / (mesh_total_ms * 1e-3), "cells_per_s": cells / (mesh_total_ms * 1e-3),
+            "mesh": {"tris_per_s": ntris_total / max(mesh_total_ms * 1e-3, 1e-9), "cells_per_s": cells / max(mesh_total_ms * 1e-3, 1e-9),
                      "classify_gbs_rank0": 4.0 * n * n * (slab.z1 - slab.z0) / (mesh_ms["classify_ms"] * 1e-3) / 1e9,
                      "note": "meshing stages only (K2-K4), slowest rank"},
             "per_rank_ms": rank_stages,

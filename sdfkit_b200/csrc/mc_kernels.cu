@@ -11,12 +11,14 @@
 //     vbase = exclusive prefix sum of per-cell created-vertex counts in visiting order;
 //   * triangle t of a cell is row entries 3t..3t+2 at  tbase[cell] + t.
 // Pipeline (one pass over the distance field, everything else is O(active cells)):
-//   K2 mc_classify  dist -> per 128-cell chunk packed counts (active, vertices, triangles)
-//   K3 mc_scan      warp-shuffle + decoupled look-back exclusive scan of the chunk counts
-//   K4a mc_compact  active chunks -> one McRecord per active cell, in visiting order
+//   K2 mc_classify  dist -> active cells per 128-cell chunk of a cell row
+//   K3 mc_scan      warp-shuffle + decoupled look-back exclusive scan of the chunk counts (run twice: record slots
+//                   after K2, vertex / triangle prefixes after K4a)
+//   K4a mc_compact  active chunks -> one McRecord per active cell, in visiting order, + full per-chunk counts
 //   K4b mc_emit     per record: triangle indices, created vertices (position, colour), normals gathered
 //                   in the reference's accumulation order, -normalize, Mesh.Transform, AABB
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mc_kernels.cuh"
@@ -48,6 +50,9 @@ __device__ const signed char d_lut[MCL_BLOB_SIZE] = MCL_BLOB_INIT;
 __device__ unsigned d_leaf[256];               // unambiguous cube index -> leaf, else MC_AMBIG
 __device__ unsigned short d_cross[256];        // cube index -> 12-bit mask of sign-changing edges
 __device__ McRowMeta d_meta[MCR_NROWS];
+// cube index -> leaf [0:15) | ambiguous [15] | vertices an INTERIOR cell creates (edges 5, 6, 10) [16:19)
+__device__ unsigned d_quick[256];
+#define MC_QUICK_AMBIG 0x8000u
 
 // edge -> corner pair (Luts.cs:26-28 in corner numbering; MarchingCubes.cs:70-71)
 __host__ __device__ static inline void mc_edge_corners(int e, int& a, int& b)
@@ -63,6 +68,7 @@ cudaError_t mc_init_tables()
     static unsigned leaf[256];
     static unsigned short cross[256];
     static McRowMeta meta[MCR_NROWS];
+    static unsigned quick[256];
     const struct { int off, rows, len; } tables[] = MCR_TABLES;
     int rid = 0;
     for (auto& t : tables) {
@@ -103,10 +109,12 @@ cudaError_t mc_init_tables()
             if (((idx >> a) ^ (idx >> b)) & 1) m |= 1u << e;
         }
         cross[idx] = (unsigned short)m;
+        quick[idx] = ((leaf[idx] & MC_AMBIG) ? MC_QUICK_AMBIG : (leaf[idx] & 0x7FFFu)) | ((unsigned)__builtin_popcount(m & 0x460u) << 16);
     }
     cudaError_t err = cudaMemcpyToSymbol(d_leaf, leaf, sizeof(leaf));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_cross, cross, sizeof(cross));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_meta, meta, sizeof(meta));
+    if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_quick, quick, sizeof(quick));
     return err;
 }
 
@@ -317,13 +325,36 @@ __device__ static inline unsigned mc_cell_leaf(const McGrid& g, const float* __r
     return leaf;
 }
 
+// leaf + packed counts of an active cell: interior unambiguous cells (nearly all) need one 256-entry table lookup,
+// cells on the i/j/k = 0 faces or with an ambiguous cube index take the out-of-line path
+__device__ __noinline__ static unsigned mc_cell_info_slow(const McGrid& g, const float* __restrict__ dist, int idx, int i, int j, int kg, unsigned* leaf_out);
+
+// quick = s_quick[idx] (the 256-entry table staged in shared memory: streaming loads evict it from L1 otherwise)
+__device__ static inline unsigned mc_cell_info(const McGrid& g, const float* __restrict__ dist, unsigned quick, int idx, int i, int j, int kg,
+                                               unsigned* leaf_out)
+{
+    if (!(quick & MC_QUICK_AMBIG) && i > 0 && j > 0 && kg > 0) {
+        *leaf_out = quick & 0x7FFFu;
+        return MC_LEAF_NT(quick) ? MC_CNT_PACK(1, (quick >> 16) & 7u, MC_LEAF_NT(quick)) : 0u;   // nt == 0 only for idx 0 / 255
+    }
+    if (idx == 0 || idx == 255) { *leaf_out = 0; return 0u; }
+    return mc_cell_info_slow(g, dist, idx, i, j, kg, leaf_out);
+}
+
 // packed (active, created vertices, triangles) of an active cell; a cell whose leaf has no triangles (the
-// reference's "impossible" case 13) emits nothing and is not recorded
+// reference's "impossible" case 13) is recorded but emits nothing
 __device__ static inline unsigned mc_cell_counts(unsigned leaf, int idx, int i, int j, int kg)
 {
-    if (MC_LEAF_NT(leaf) == 0u) return 0u;
+    if (MC_LEAF_NT(leaf) == 0u) return MC_CNT_PACK(1, 0, 0);
     const unsigned nv = __popc((unsigned)d_cross[idx] & mc_owned_mask(i, j, kg)) + MC_LEAF_CENTER(leaf);
     return MC_CNT_PACK(1, nv, MC_LEAF_NT(leaf));
+}
+
+__device__ __noinline__ static unsigned mc_cell_info_slow(const McGrid& g, const float* __restrict__ dist, int idx, int i, int j, int kg, unsigned* leaf_out)
+{
+    const unsigned leaf = mc_cell_leaf(g, dist, idx, i, j, kg);
+    *leaf_out = leaf;
+    return mc_cell_counts(leaf, idx, i, j, kg);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -384,13 +415,14 @@ __device__ static inline int mc_cube_index(unsigned lo0, unsigned lo1, unsigned 
 
 // ---------------------------------------------------------------------------------------------------
 // K2 mc_classify: one warp marches a 128-cell x-chunk by MC_R rows through MC_K layers; every voxel's
-// sign is computed once per march (x/y/z halos aside) and only packed per-chunk counts are written.
+// sign is computed once per march (x/y/z halos aside).  Output: the number of ACTIVE CELLS of every chunk -- pure
+// streaming + bit tricks; everything that needs a cube index (leaf, vertex / triangle counts) is left to K4a, which
+// only visits the active chunks, and a second run of the scan.
 // ---------------------------------------------------------------------------------------------------
-#define MC_R 8
 #define MC_K 16
 #define MC_CLASSIFY_WARPS 8
 
-template <bool VEC>
+template <bool VEC, int MC_R>
 __device__ static inline void mc_plane_signs(const float* __restrict__ plane, size_t row_stride, int nrows, int nx, int step,
                                              float iso, int i0, unsigned lane, unsigned* out)
 {
@@ -401,15 +433,51 @@ __device__ static inline void mc_plane_signs(const float* __restrict__ plane, si
     for (int r = 0; r <= MC_R; r++) out[r] = mc_row_bits<VEC>(ld[r], iso, nx, step, i0, lane);
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(MC_CLASSIFY_WARPS * 32)
+// 0xFFFFFFFF if a > b (ordered: false for NaN) else 0 -- one FSET, no predicate/select pair
+__device__ static inline unsigned mc_gt_mask(float a, float b)
+{
+    unsigned m;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+    return m;
+}
+
+// Vector path (step 1, nx % 4 == 0) of one plane: the voxel arrays are padded, so every lane loads unconditionally
+// (MC_R + 1) x (LDG.128 + the right-neighbour LDG.32) back to back, then turns them into 5-bit sign words.
+// lp = this lane's pointer to voxel (i0, row 0) of the plane; vm = 0xF for lanes inside the row, else 0.
+template <int MC_R>
+__device__ static inline void mc_plane_signs_vec(const float* __restrict__ lp, unsigned row_stride, int eoff, bool e_ok, unsigned vm,
+                                                 float iso, unsigned lane, unsigned* out)
+{
+    float4 q[MC_R + 1];
+    float e[MC_R + 1];
+#pragma unroll
+    for (int r = 0; r <= MC_R; r++) {
+        const float* rp = lp + (size_t)r * row_stride;
+        q[r] = __ldg(reinterpret_cast<const float4*>(rp));
+        e[r] = __ldg(rp + eoff);
+    }
+#pragma unroll
+    for (int r = 0; r <= MC_R; r++) {
+        const unsigned m0 = mc_gt_mask(q[r].x, iso), m1 = mc_gt_mask(q[r].y, iso), m2 = mc_gt_mask(q[r].z, iso), m3 = mc_gt_mask(q[r].w, iso);
+        unsigned s = (m0 & 1u) | (m1 & ~1u);
+        s = (s & 3u) | (m2 & ~3u);
+        s = (s & 7u) | (m3 & ~7u);
+        s &= vm;
+        unsigned nb = __shfl_down_sync(FULL, s, 1);
+        if (lane == 31u) nb = (e_ok && e[r] > iso) ? 1u : 0u;
+        out[r] = s | ((nb & 1u) << 4);
+    }
+}
+
+template <bool VEC, int MC_R, int MINB>
+__global__ void __launch_bounds__(MC_CLASSIFY_WARPS * 32, MINB)
 mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
                    unsigned njb, unsigned nkb, unsigned ntiles)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = blockIdx.x * MC_CLASSIFY_WARPS + (threadIdx.x >> 5);
     const unsigned nw = gridDim.x * MC_CLASSIFY_WARPS;
-    const int nx = g.nx, step = g.step, ncx = g.ncx, ncy = g.ncy, cpr = g.cpr;
+    const int nx = g.nx, step = g.step, ncy = g.ncy, cpr = g.cpr;
     const float iso = g.iso;
     const size_t row_stride = (size_t)step * (size_t)nx;                // floats between voxel rows y and y+step
     const size_t plane_stride = (size_t)g.ny * (size_t)nx;              // floats per z slice
@@ -426,41 +494,65 @@ mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __r
         const int nlay = min(MC_K, g.nk - kl0);
         const float* plane = dist + (size_t)((g.k0 + kl0) * step - g.z0) * plane_stride + (size_t)j0 * row_stride;
         unsigned* cnt_out = counts + ((size_t)kl0 * ncy + j0) * cpr + xc;
+        // vector path constants
+        const int eoff = (lane == 31u) ? 4 : 3;
+        const bool e_ok = i0 + 4 < nx;
+        const unsigned vm = (i0 < nx) ? 0xFu : 0u;
+        // cells of this lane that exist (i0 + c < ncx), replicated into the 5-bit row fields 0..MC_R-1
+        const unsigned c4 = (i0 + 3 < g.ncx) ? 15u : (i0 < g.ncx ? ((1u << (g.ncx - i0)) - 1u) : 0u);
+        const unsigned long long cellmask = (unsigned long long)c4 * (0x10842108421ull & ((1ull << (5 * nrows)) - 1ull));
 
         unsigned prev[MC_R + 1], cur[MC_R + 1];
-        mc_plane_signs<VEC>(plane, row_stride, nrows, nx, step, iso, i0, lane, prev);
+        if (VEC) mc_plane_signs_vec<MC_R>(plane + i0, (unsigned)nx, eoff, e_ok, vm, iso, lane, prev);
+        else mc_plane_signs<false, MC_R>(plane, row_stride, nrows, nx, step, iso, i0, lane, prev);
+        unsigned por = 0u, pand = 31u;                                  // OR / AND over the lane's sign words of the lower plane
+#pragma unroll
+        for (int r = 0; r <= MC_R; r++) { por |= prev[r]; pand &= prev[r]; }
+#pragma unroll 1
         for (int kk = 0; kk < nlay; kk++) {
             plane += (size_t)step * plane_stride;
-            mc_plane_signs<VEC>(plane, row_stride, nrows, nx, step, iso, i0, lane, cur);
-            const int kg = g.k0 + kl0 + kk;
+            if (VEC) mc_plane_signs_vec<MC_R>(plane + i0, (unsigned)nx, eoff, e_ok, vm, iso, lane, cur);
+            else mc_plane_signs<false, MC_R>(plane, row_stride, nrows, nx, step, iso, i0, lane, cur);
+            unsigned cor = 0u, cand = 31u;
 #pragma unroll
-            for (int r = 0; r < MC_R; r++) {
-                const unsigned lo0 = prev[r], lo1 = prev[r + 1], hi0 = cur[r], hi1 = cur[r + 1];
-                unsigned cnt = 0;
-                const unsigned any = lo0 | lo1 | hi0 | hi1, all = lo0 & lo1 & hi0 & hi1;
-                if (any != 0u && all != 31u && r < nrows) {             // rare: the lane's 4 cells are not all empty / all full
-                    const int j = j0 + r;
+            for (int r = 0; r <= MC_R; r++) { cor |= cur[r]; cand &= cur[r]; }
+            // no lane of the warp sees a sign change in its 4 x 8 cells of this layer (the common case): 8 zero counts
+            const bool quiet = ((por | cor) == 0u) || ((pand & cand) == 31u);
+            if (__all_sync(FULL, quiet)) {
+                if ((int)lane < nrows) cnt_out[(size_t)lane * cpr] = 0u;
+            } else {
+                // count the ACTIVE CELLS of every row, all rows at once on packed words (field r = 5 bits of row r):
+                // cell c of row r is active unless its 8 corner signs are all 0 or all 1
+                unsigned long long prevp = 0ull, curp = 0ull;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int idx = mc_cube_index(lo0, lo1, hi0, hi1, c);
-                        const int i = i0 + c;
-                        if (i < ncx && idx != 0 && idx != 255) cnt += mc_cell_counts(mc_cell_leaf(g, dist, idx, i, j, kg), idx, i, j, kg);
-                    }
+                for (int r = 0; r <= MC_R; r++) { prevp |= (unsigned long long)prev[r] << (5 * r); curp |= (unsigned long long)cur[r] << (5 * r); }
+                unsigned long long anyp = prevp | curp, allp = prevp & curp;
+                anyp |= anyp >> 5;                                       // rows r, r+1 x both planes
+                allp &= allp >> 5;
+                anyp |= anyp >> 1;                                       // voxels c, c+1
+                allp &= allp >> 1;
+                const unsigned long long actp = anyp & ~allp & cellmask;
+                unsigned mine = 0;
+#pragma unroll
+                for (int r = 0; r < MC_R; r++) {
+                    const unsigned t = __reduce_add_sync(FULL, __popc((unsigned)(actp >> (5 * r)) & 15u));
+                    if (lane == (unsigned)r) mine = t;
                 }
-                const unsigned total = __reduce_add_sync(FULL, cnt);
-                if (lane == 0 && r < nrows) cnt_out[(size_t)r * cpr] = total;
+                if ((int)lane < nrows) cnt_out[(size_t)lane * cpr] = mine;
             }
             cnt_out += (size_t)ncy * cpr;
 #pragma unroll
             for (int r = 0; r <= MC_R; r++) prev[r] = cur[r];
+            por = cor;
+            pand = cand;
         }
     }
 }
 
-cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s)
+template <bool VEC, int R, int MINB>
+static cudaError_t mc_launch_classify_t(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s)
 {
-    if (g.nchunks == 0) return cudaSuccess;
-    const unsigned njb = (g.ncy + MC_R - 1) / MC_R, nkb = (g.nk + MC_K - 1) / MC_K;
+    const unsigned njb = (g.ncy + R - 1) / R, nkb = (g.nk + MC_K - 1) / MC_K;
     const unsigned long long nt = (unsigned long long)g.cpr * njb * nkb;
     if (nt > 0xFFFFFFFFull) return cudaErrorInvalidValue;
     const unsigned ntiles = (unsigned)nt;
@@ -470,10 +562,16 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
     unsigned blocks = (ntiles + MC_CLASSIFY_WARPS - 1) / MC_CLASSIFY_WARPS;
     const unsigned maxb = (unsigned)sms * 8u;
     if (blocks > maxb) blocks = maxb;
-    const bool vec = g.step == 1 && (g.nx & 3) == 0 && g.nx >= 4;
-    if (vec) mc_classify_kernel<true><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
-    else mc_classify_kernel<false><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
+    mc_classify_kernel<VEC, R, MINB><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
     return cudaGetLastError();
+}
+
+cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s)
+{
+    if (g.nchunks == 0) return cudaSuccess;
+    const bool vec = g.step == 1 && (g.nx & 3) == 0 && g.nx >= 4;
+    if (!vec) return mc_launch_classify_t<false, 8, 1>(g, dist, counts, s);
+    return mc_launch_classify_t<true, 8, 2>(g, dist, counts, s);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -607,9 +705,12 @@ cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks
 // ---------------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned* __restrict__ counts,
+mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
                   const uint4* __restrict__ base, McRecord* __restrict__ recs, uint4* __restrict__ masks)
 {
+    __shared__ unsigned s_quick[256];
+    s_quick[threadIdx.x & 255u] = d_quick[threadIdx.x & 255u];
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned nw = (gridDim.x * blockDim.x) >> 5;
@@ -638,16 +739,17 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
             const unsigned hi0 = mc_row_bits<VEC>(l10, iso, nx, step, i0, lane), hi1 = mc_row_bits<VEC>(l11, iso, nx, step, i0, lane);
             unsigned leaf[4], cnt[4];
             unsigned tot = 0;
+            int idx[4];
+            unsigned q[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) idx[c] = mc_cube_index(lo0, lo1, hi0, hi1, c);
+#pragma unroll
+            for (int c = 0; c < 4; c++) q[c] = s_quick[idx[c]];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 leaf[c] = 0;
                 cnt[c] = 0;
-                const int idx = mc_cube_index(lo0, lo1, hi0, hi1, c);
-                const int i = i0 + c;
-                if (i < g.ncx && idx != 0 && idx != 255) {
-                    leaf[c] = mc_cell_leaf(g, dist, idx, i, j, kg);
-                    cnt[c] = mc_cell_counts(leaf[c], idx, i, j, kg);
-                }
+                if (i0 + c < g.ncx) cnt[c] = mc_cell_info(g, dist, q[c], idx[c], i0 + c, j, kg, &leaf[c]);
                 tot += cnt[c];
             }
             const uint4 m = make_uint4(__ballot_sync(FULL, cnt[0] != 0u), __ballot_sync(FULL, cnt[1] != 0u),
@@ -661,6 +763,7 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
                 if (lane >= (unsigned)d) inc += t;
             }
             unsigned run = inc - tot;
+            if (lane == 31u) counts[chunk] = inc;                        // the chunk's full packed counts, for the second scan
             const uint4 b = base[chunk];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -668,8 +771,8 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
                     McRecord r;
                     r.cell = (unsigned)(i0 + c) + (unsigned)g.ncx * ((unsigned)j + (unsigned)g.ncy * (unsigned)kl);
                     r.info = leaf[c];
-                    r.vbase = b.y + MC_CNT_V(run);
-                    r.tbase = b.z + MC_CNT_T(run);
+                    r.vbase = MC_CNT_V(run);                              // chunk-local; + base[chunk].y / .z after the second scan
+                    r.tbase = MC_CNT_T(run);
                     const McRowMeta* mt = d_meta + MC_LEAF_ROW(leaf[c]);
                     const unsigned own = mc_owned_mask(i0 + c, j, kg) & mt->refmask;
                     r.aux = mt->occ_packed | (unsigned long long)(__popc(mt->before[5] & own) | (__popc(mt->before[6] & own) << 4) |
@@ -683,7 +786,7 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
     }
 }
 
-cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
                               McRecord* recs, uint4* masks, cudaStream_t s)
 {
     if (g.nchunks == 0) return cudaSuccess;
@@ -707,11 +810,12 @@ cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned
 #define MC_EMIT_THREADS 128
 
 // index of the record of cell (i, j, kl), -1 if that cell is not active
-__device__ static inline int mc_find_record(const McEmitParams& p, int i, int j, int kl)
+__device__ static inline int mc_find_record(const McEmitParams& p, int i, int j, int kl, unsigned* chunk_vbase = nullptr)
 {
     const McGrid& g = p.g;
     const unsigned chunk = ((unsigned)kl * (unsigned)g.ncy + (unsigned)j) * (unsigned)g.cpr + ((unsigned)i >> 7);
     const uint4 b = __ldg(p.base + chunk);
+    if (chunk_vbase) *chunk_vbase = b.y;
     const uint4 m = __ldg(p.masks + chunk);       // garbage for inactive chunks: only used when the count says active
     if (MC_CNT_ACT(b.w) == 0u) return -1;
     const unsigned l = ((unsigned)i & 127u) >> 2, c = (unsigned)i & 3u;
@@ -824,10 +928,13 @@ __device__ static inline int mc_vertex_id(const McEmitParams& p, const McRecord&
     int di, dj, dk, e2;
     mc_creator_of<E>(i, j, kg, di, dj, dk, e2);
     const int oi = i + di, oj = j + dj, okl = kl + dk;
-    const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl) : -1;
+    unsigned cvb = 0;
+    const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl, &cvb) : -1;
     if (orr < 0) { atomicExch(p.error_flag, 1); return 0; }
     const McRecord* orp = p.recs + orr;
-    const uint4 oa = __ldg(reinterpret_cast<const uint4*>(orp));            // cell, info, vbase, tbase
+    uint4 oa = __ldg(reinterpret_cast<const uint4*>(orp));                  // cell, info, vbase (chunk-local), tbase
+    oa.z += cvb;
+    if (MC_LEAF_NT(oa.y) == 0u) { atomicExch(p.error_flag, 5); return 0; }   // creator is an "impossible case 13" cell
     const unsigned long long aux = __ldg(&orp->aux);
     if (e2 == 5) return (int)(oa.z + MC_AUX_RANK(aux, 0));
     if (e2 == 6) return (int)(oa.z + MC_AUX_RANK(aux, 1));
@@ -952,17 +1059,22 @@ mc_emit_kernel(const McEmitParams p)
     const unsigned r = p.rec_begin + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
     if (r < p.rec_end) {
-        const McRecord rec = p.recs[r];
+        McRecord rec = p.recs[r];
         const int i = (int)(rec.cell % (unsigned)g.ncx);
         const unsigned t2 = rec.cell / (unsigned)g.ncx;
         const int j = (int)(t2 % (unsigned)g.ncy);
         const int kl = (int)(t2 / (unsigned)g.ncy);
         const int kg = g.k0 + kl;
+        {   // records carry chunk-local offsets
+            const uint4 cb = __ldg(p.base + (t2 * (unsigned)g.cpr + ((unsigned)i >> 7)));
+            rec.vbase += cb.y;
+            rec.tbase += cb.z;
+        }
         const McRowMeta* meta = d_meta + MC_LEAF_ROW(rec.info);
         const signed char* row = d_lut + meta->off;
         const int nent = 3 * (int)MC_LEAF_NT(rec.info);
         const unsigned owned = mc_owned_mask(i, j, kg);
-        const unsigned refd = meta->refmask;
+        const unsigned refd = nent ? meta->refmask : 0u;                // nent == 0: "impossible case 13", emits nothing
         int* vid = s_vid[threadIdx.x];
 
         double v[8];

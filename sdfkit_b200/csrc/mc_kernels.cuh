@@ -24,8 +24,8 @@ struct McGrid {
 struct __align__(32) McRecord {
     unsigned cell;         // local linear cell id: i + ncx*(j + ncy*(k - k0))
     unsigned info;         // leaf: tiling row id [0:10) | ntris [10:14) | uses centre vertex [14]
-    unsigned vbase;        // exclusive prefix of created vertices (slab-local)
-    unsigned tbase;        // exclusive prefix of triangles (slab-local)
+    unsigned vbase;        // created vertices before this cell INSIDE ITS CHUNK (+ base[chunk].y = slab-local prefix)
+    unsigned tbase;        // triangles before this cell inside its chunk (+ base[chunk].z)
     unsigned long long aux;   // what neighbours ask of this cell, so that a lookup is one 32-byte read:
                               //   [0:16)  creation rank of slots 5, 6, 10, 12 (4 bits each) -> vertex id = vbase + rank
                               //   [16:52) how often the row references edge e = 0..11 (3 bits each)
@@ -66,12 +66,16 @@ struct McEmitParams {
     int* error_flag;
 };
 
+// The vector path of mc_classify reads up to MC_PAD_ROWS voxel rows (+ a few floats) past the rows it needs;
+// voxel arrays are allocated with that much padding so those loads need no clamping.
+#define MC_PAD_ROWS 10
+
 // host-side launchers (mc_kernels.cu)
 cudaError_t mc_init_tables();
 cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s);
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
                            McTotals* totals, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);
-cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
                               McRecord* recs, uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);
