@@ -406,12 +406,6 @@ __device__ static inline unsigned mc_row_bits(const McRowLoad& r, float iso, int
     return s;
 }
 
-// cube index of cell c (0..3) of a lane from the 5-bit sign rows (lo = plane z, hi = plane z+step; 0 = row y, 1 = row y+step)
-__device__ static inline int mc_cube_index(unsigned lo0, unsigned lo1, unsigned hi0, unsigned hi1, int c)
-{
-    return (int)(((lo0 >> c) & 3u) | (((lo1 >> (c + 1)) & 1u) << 2) | (((lo1 >> c) & 1u) << 3) |
-                 (((hi0 >> c) & 3u) << 4) | (((hi1 >> (c + 1)) & 1u) << 6) | (((hi1 >> c) & 1u) << 7));
-}
 
 // ---------------------------------------------------------------------------------------------------
 // K2 mc_classify: one warp marches a 128-cell x-chunk by MC_R rows through MC_K layers; every voxel's
@@ -471,7 +465,7 @@ __device__ static inline void mc_plane_signs_vec(const float* __restrict__ lp, u
 
 template <bool VEC, int MC_R, int MINB>
 __global__ void __launch_bounds__(MC_CLASSIFY_WARPS * 32, MINB)
-mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
+mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts, uint4* __restrict__ masks,
                    unsigned njb, unsigned nkb, unsigned ntiles)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -494,6 +488,7 @@ mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __r
         const int nlay = min(MC_K, g.nk - kl0);
         const float* plane = dist + (size_t)((g.k0 + kl0) * step - g.z0) * plane_stride + (size_t)j0 * row_stride;
         unsigned* cnt_out = counts + ((size_t)kl0 * ncy + j0) * cpr + xc;
+        uint4* mask_out = masks + ((size_t)kl0 * ncy + j0) * cpr + xc;
         // vector path constants
         const int eoff = (lane == 31u) ? 4 : 3;
         const bool e_ok = i0 + 4 < nx;
@@ -532,15 +527,26 @@ mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __r
                 anyp |= anyp >> 1;                                       // voxels c, c+1
                 allp &= allp >> 1;
                 const unsigned long long actp = anyp & ~allp & cellmask;
+                // per row: the count, and the chunk's 128-bit activity mask in natural cell order (bit 4*lane + c):
+                // word w = OR of the nibbles of lanes 8w .. 8w+7 (xor-shuffle tree inside each group of 8 lanes)
                 unsigned mine = 0;
+                const unsigned sh = 4u * (lane & 7u);
+                unsigned* mw = reinterpret_cast<unsigned*>(mask_out) + (lane >> 3);
 #pragma unroll
                 for (int r = 0; r < MC_R; r++) {
-                    const unsigned t = __reduce_add_sync(FULL, __popc((unsigned)(actp >> (5 * r)) & 15u));
+                    const unsigned nib = (unsigned)(actp >> (5 * r)) & 15u;
+                    const unsigned t = __reduce_add_sync(FULL, __popc(nib));
                     if (lane == (unsigned)r) mine = t;
+                    unsigned w = nib << sh;
+                    w |= __shfl_xor_sync(FULL, w, 1);
+                    w |= __shfl_xor_sync(FULL, w, 2);
+                    w |= __shfl_xor_sync(FULL, w, 4);
+                    if ((lane & 7u) == 0u && r < nrows) mw[(size_t)r * cpr * 4] = w;
                 }
                 if ((int)lane < nrows) cnt_out[(size_t)lane * cpr] = mine;
             }
             cnt_out += (size_t)ncy * cpr;
+            mask_out += (size_t)ncy * cpr;
 #pragma unroll
             for (int r = 0; r <= MC_R; r++) prev[r] = cur[r];
             por = cor;
@@ -550,7 +556,7 @@ mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __r
 }
 
 template <bool VEC, int R, int MINB>
-static cudaError_t mc_launch_classify_t(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s)
+static cudaError_t mc_launch_classify_t(const McGrid& g, const float* dist, unsigned* counts, uint4* masks, cudaStream_t s)
 {
     const unsigned njb = (g.ncy + R - 1) / R, nkb = (g.nk + MC_K - 1) / MC_K;
     const unsigned long long nt = (unsigned long long)g.cpr * njb * nkb;
@@ -562,16 +568,16 @@ static cudaError_t mc_launch_classify_t(const McGrid& g, const float* dist, unsi
     unsigned blocks = (ntiles + MC_CLASSIFY_WARPS - 1) / MC_CLASSIFY_WARPS;
     const unsigned maxb = (unsigned)sms * 8u;
     if (blocks > maxb) blocks = maxb;
-    mc_classify_kernel<VEC, R, MINB><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, njb, nkb, ntiles);
+    mc_classify_kernel<VEC, R, MINB><<<blocks, MC_CLASSIFY_WARPS * 32, 0, s>>>(g, dist, counts, masks, njb, nkb, ntiles);
     return cudaGetLastError();
 }
 
-cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s)
+cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, uint4* masks, cudaStream_t s)
 {
     if (g.nchunks == 0) return cudaSuccess;
     const bool vec = g.step == 1 && (g.nx & 3) == 0 && g.nx >= 4;
-    if (!vec) return mc_launch_classify_t<false, 8, 1>(g, dist, counts, s);
-    return mc_launch_classify_t<true, 8, 2>(g, dist, counts, s);
+    if (!vec) return mc_launch_classify_t<false, 8, 1>(g, dist, counts, masks, s);
+    return mc_launch_classify_t<true, 8, 2>(g, dist, counts, masks, s);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -699,14 +705,35 @@ cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4a mc_compact: re-classify the active chunks and write one record per active cell, in visiting order,
-// plus the chunk's 128-bit activity mask (4 ballots: bit l of word c <-> cell 4*l + c) that makes the
-// record of any cell an O(1) lookup:  base[chunk].x + rank(mask, cell).
+// K4a mc_compact: one LANE per active cell.  A warp takes 32 consecutive chunks, lists their active cells (chunk
+// by chunk, cell order inside a chunk -- i.e. visiting order) from the activity masks K2 wrote, and hands one cell
+// to every lane: 8 corner loads, cube index, leaf (256-entry table; FP64 tests for the ambiguous cases), created
+// vertices / triangles, and a segmented warp scan that yields the cell's offsets inside its chunk.  Writes the
+// 32-byte record at base[chunk].x + (rank in chunk) and, per chunk, the full packed counts for the second scan.
 // ---------------------------------------------------------------------------------------------------
-template <bool VEC>
+__device__ static inline int mc_nth_set_bit(uint4 m, unsigned n)   // position (0..127) of the n-th (0-based) set bit
+{
+    unsigned c = __popc(m.x);
+    if (n < c) return (int)__fns(m.x, 0, (int)n + 1);
+    n -= c; c = __popc(m.y);
+    if (n < c) return 32 + (int)__fns(m.y, 0, (int)n + 1);
+    n -= c; c = __popc(m.z);
+    if (n < c) return 64 + (int)__fns(m.z, 0, (int)n + 1);
+    n -= c;
+    return 96 + (int)__fns(m.w, 0, (int)n + 1);
+}
+
+__device__ static inline unsigned long long mc_record_aux(unsigned leaf, int i, int j, int kg)
+{
+    const McRowMeta* mt = d_meta + MC_LEAF_ROW(leaf);
+    const unsigned own = mc_owned_mask(i, j, kg) & mt->refmask;
+    return mt->occ_packed | (unsigned long long)(__popc(mt->before[5] & own) | (__popc(mt->before[6] & own) << 4) |
+                                                 (__popc(mt->before[10] & own) << 8) | (__popc(mt->before[12] & own) << 12));
+}
+
 __global__ void __launch_bounds__(256)
 mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
-                  const uint4* __restrict__ base, McRecord* __restrict__ recs, uint4* __restrict__ masks)
+                  const uint4* __restrict__ base, McRecord* __restrict__ recs, const uint4* __restrict__ masks)
 {
     __shared__ unsigned s_quick[256];
     s_quick[threadIdx.x & 255u] = d_quick[threadIdx.x & 255u];
@@ -714,80 +741,92 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __re
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned nw = (gridDim.x * blockDim.x) >> 5;
-    const int nx = g.nx, step = g.step;
     const float iso = g.iso;
-    const size_t row_stride = (size_t)step * (size_t)nx;
-    const size_t plane_stride = (size_t)g.ny * (size_t)nx;
     for (unsigned c0 = gw * 32u; c0 < g.nchunks; c0 += nw * 32u) {
-        const unsigned mine = (c0 + lane < g.nchunks) ? MC_CNT_ACT(counts[c0 + lane]) : 0u;
-        unsigned todo = __ballot_sync(FULL, mine != 0u);
-        while (todo) {
-            const unsigned chunk = c0 + (unsigned)(__ffs(todo) - 1);
-            todo &= todo - 1;
-            const unsigned xc = chunk % (unsigned)g.cpr;
-            const unsigned row = chunk / (unsigned)g.cpr;
-            const int j = (int)(row % (unsigned)g.ncy);
-            const int kl = (int)(row / (unsigned)g.ncy);
-            const int kg = g.k0 + kl;
-            const int i0 = (int)(xc * 128u + lane * 4u);
-            const float* p00 = dist + (size_t)(kg * step - g.z0) * plane_stride + (size_t)j * row_stride;
-            const McRowLoad l00 = mc_row_load<VEC>(p00, nx, step, i0, lane);
-            const McRowLoad l01 = mc_row_load<VEC>(p00 + row_stride, nx, step, i0, lane);
-            const McRowLoad l10 = mc_row_load<VEC>(p00 + (size_t)step * plane_stride, nx, step, i0, lane);
-            const McRowLoad l11 = mc_row_load<VEC>(p00 + (size_t)step * plane_stride + row_stride, nx, step, i0, lane);
-            const unsigned lo0 = mc_row_bits<VEC>(l00, iso, nx, step, i0, lane), lo1 = mc_row_bits<VEC>(l01, iso, nx, step, i0, lane);
-            const unsigned hi0 = mc_row_bits<VEC>(l10, iso, nx, step, i0, lane), hi1 = mc_row_bits<VEC>(l11, iso, nx, step, i0, lane);
-            unsigned leaf[4], cnt[4];
-            unsigned tot = 0;
-            int idx[4];
-            unsigned q[4];
+        // lane L looks after chunk c0 + L
+        const unsigned myc = c0 + lane;
+        const unsigned nact = (myc < g.nchunks) ? MC_CNT_ACT(counts[myc]) : 0u;
+        unsigned incl = nact;
 #pragma unroll
-            for (int c = 0; c < 4; c++) idx[c] = mc_cube_index(lo0, lo1, hi0, hi1, c);
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const unsigned total = __shfl_sync(FULL, incl, 31);
+        if (total == 0u) continue;
+        const unsigned pre = incl - nact;                         // items of the chunks before mine
+        uint4 mymask = make_uint4(0, 0, 0, 0);
+        unsigned myslot = 0;
+        if (nact) { mymask = masks[myc]; myslot = base[myc].x; }
+        unsigned carry = 0;                                       // packed counts of the leading chunk's items in earlier batches
+        for (unsigned b = 0; b < total; b += 32u) {
+            const unsigned t = b + lane;
+            const bool valid = t < total;
+            // owner lane: the last L with pre_L <= t and nact_L > 0  ==  (number of lanes with incl_L <= t)
+            unsigned lo = 0;
 #pragma unroll
-            for (int c = 0; c < 4; c++) q[c] = s_quick[idx[c]];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                leaf[c] = 0;
-                cnt[c] = 0;
-                if (i0 + c < g.ncx) cnt[c] = mc_cell_info(g, dist, q[c], idx[c], i0 + c, j, kg, &leaf[c]);
-                tot += cnt[c];
+            for (int step = 16; step > 0; step >>= 1) {
+                const unsigned probe = lo + (unsigned)step - 1u;   // lanes [lo, probe] all have incl <= t ?
+                const unsigned v = __shfl_sync(FULL, incl, probe & 31u);
+                if (probe < 32u && v <= t) lo += (unsigned)step;
             }
-            const uint4 m = make_uint4(__ballot_sync(FULL, cnt[0] != 0u), __ballot_sync(FULL, cnt[1] != 0u),
-                                       __ballot_sync(FULL, cnt[2] != 0u), __ballot_sync(FULL, cnt[3] != 0u));
-            if (lane == 0) masks[chunk] = m;
-            // exclusive warp scan of the packed (act | verts | tris) counts; fields cannot overflow inside a chunk
-            unsigned inc = tot;
+            const unsigned src = valid ? min(lo, 31u) : 0u;
+            const unsigned spre = __shfl_sync(FULL, pre, src), snact = __shfl_sync(FULL, nact, src), sslot = __shfl_sync(FULL, myslot, src);
+            uint4 sm;
+            sm.x = __shfl_sync(FULL, mymask.x, src); sm.y = __shfl_sync(FULL, mymask.y, src);
+            sm.z = __shfl_sync(FULL, mymask.z, src); sm.w = __shfl_sync(FULL, mymask.w, src);
+            unsigned cnt = 0, leaf = 0, q = 0;
+            int i = 0, j = 0, kl = 0;
+            if (valid) {
+                q = t - spre;                                     // rank of my cell among the chunk's active cells
+                const unsigned chunk = c0 + src;
+                const unsigned xc = chunk % (unsigned)g.cpr, row = chunk / (unsigned)g.cpr;
+                j = (int)(row % (unsigned)g.ncy);
+                kl = (int)(row / (unsigned)g.ncy);
+                i = (int)(xc * 128u) + mc_nth_set_bit(sm, q);
+                const int kg = g.k0 + kl;
+                float f[8];
+                f[0] = __ldg(dist + mc_vox(g, i, j, kg, 0, 0, 0)); f[1] = __ldg(dist + mc_vox(g, i, j, kg, 1, 0, 0));
+                f[2] = __ldg(dist + mc_vox(g, i, j, kg, 1, 1, 0)); f[3] = __ldg(dist + mc_vox(g, i, j, kg, 0, 1, 0));
+                f[4] = __ldg(dist + mc_vox(g, i, j, kg, 0, 0, 1)); f[5] = __ldg(dist + mc_vox(g, i, j, kg, 1, 0, 1));
+                f[6] = __ldg(dist + mc_vox(g, i, j, kg, 1, 1, 1)); f[7] = __ldg(dist + mc_vox(g, i, j, kg, 0, 1, 1));
+                int idx = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) idx |= (f[k] > iso ? 1 : 0) << k;
+                cnt = mc_cell_info(g, dist, s_quick[idx], idx, i, j, kg, &leaf);
+            }
+            // segmented scan: exclusive sum of cnt over the earlier items of the same chunk
+            unsigned sc = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const unsigned t = __shfl_up_sync(FULL, inc, d);
-                if (lane >= (unsigned)d) inc += t;
+                const unsigned v = __shfl_up_sync(FULL, sc, d);
+                if (lane >= (unsigned)d) sc += v;
             }
-            unsigned run = inc - tot;
-            if (lane == 31u) counts[chunk] = inc;                        // the chunk's full packed counts, for the second scan
-            const uint4 b = base[chunk];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if (cnt[c]) {
-                    McRecord r;
-                    r.cell = (unsigned)(i0 + c) + (unsigned)g.ncx * ((unsigned)j + (unsigned)g.ncy * (unsigned)kl);
-                    r.info = leaf[c];
-                    r.vbase = MC_CNT_V(run);                              // chunk-local; + base[chunk].y / .z after the second scan
-                    r.tbase = MC_CNT_T(run);
-                    const McRowMeta* mt = d_meta + MC_LEAF_ROW(leaf[c]);
-                    const unsigned own = mc_owned_mask(i0 + c, j, kg) & mt->refmask;
-                    r.aux = mt->occ_packed | (unsigned long long)(__popc(mt->before[5] & own) | (__popc(mt->before[6] & own) << 4) |
-                                                                   (__popc(mt->before[10] & own) << 8) | (__popc(mt->before[12] & own) << 12));
-                    r.pad = 0;
-                    recs[b.x + MC_CNT_ACT(run)] = r;
-                    run += cnt[c];
-                }
+            const unsigned excl = sc - cnt;                        // exclusive over the whole batch
+            const int seg0 = (int)spre - (int)b;                   // lane of my chunk's first item (< 0: it started in an earlier batch)
+            const unsigned at0 = __shfl_sync(FULL, excl, seg0 > 0 ? seg0 : 0);
+            const unsigned within = excl - at0 + (seg0 < 0 ? carry : 0u);   // packed (act | verts | tris) before me in my chunk
+            if (valid) {
+                const int kg = g.k0 + kl;
+                McRecord r;
+                r.cell = (unsigned)i + (unsigned)g.ncx * ((unsigned)j + (unsigned)g.ncy * (unsigned)kl);
+                r.info = leaf;
+                r.vbase = MC_CNT_V(within);
+                r.tbase = MC_CNT_T(within);
+                r.aux = mc_record_aux(leaf, i, j, kg);
+                r.pad = 0;
+                recs[sslot + q] = r;
+                if (q + 1u == snact) counts[c0 + src] = within + cnt;   // last cell of the chunk: its full packed counts
             }
+            // carry for a chunk that continues into the next batch: totals of its items seen so far
+            const unsigned last_within = __shfl_sync(FULL, within + cnt, 31);
+            carry = last_within;
         }
     }
 }
 
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
-                              McRecord* recs, uint4* masks, cudaStream_t s)
+                              McRecord* recs, const uint4* masks, cudaStream_t s)
 {
     if (g.nchunks == 0) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -796,9 +835,7 @@ cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* coun
     unsigned groups = (g.nchunks + 31u) / 32u;
     unsigned blocks = (groups + 7u) / 8u;
     if (blocks > (unsigned)sms * 8u) blocks = (unsigned)sms * 8u;
-    const bool vec = g.step == 1 && (g.nx & 3) == 0 && g.nx >= 4;
-    if (vec) mc_compact_kernel<true><<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks);
-    else mc_compact_kernel<false><<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks);
+    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks);
     return cudaGetLastError();
 }
 
@@ -818,14 +855,13 @@ __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j,
     if (chunk_vbase) *chunk_vbase = b.y;
     const uint4 m = __ldg(p.masks + chunk);       // garbage for inactive chunks: only used when the count says active
     if (MC_CNT_ACT(b.w) == 0u) return -1;
-    const unsigned l = ((unsigned)i & 127u) >> 2, c = (unsigned)i & 3u;
-    const unsigned wc = c == 0 ? m.x : (c == 1 ? m.y : (c == 2 ? m.z : m.w));
-    if (!((wc >> l) & 1u)) return -1;
-    const unsigned below = (1u << l) - 1u;
-    unsigned rank = __popc(m.x & below) + __popc(m.y & below) + __popc(m.z & below) + __popc(m.w & below);
-    if (c > 0) rank += (m.x >> l) & 1u;
-    if (c > 1) rank += (m.y >> l) & 1u;
-    if (c > 2) rank += (m.z >> l) & 1u;
+    const unsigned q = (unsigned)i & 127u, w = q >> 5, bit = q & 31u;      // natural order: bit q of the 128-bit mask
+    const unsigned ww = w == 0 ? m.x : (w == 1 ? m.y : (w == 2 ? m.z : m.w));
+    if (!((ww >> bit) & 1u)) return -1;
+    unsigned rank = __popc(ww & ((1u << bit) - 1u));
+    if (w > 0) rank += __popc(m.x);
+    if (w > 1) rank += __popc(m.y);
+    if (w > 2) rank += __popc(m.z);
     return (int)(b.x + rank);
 }
 

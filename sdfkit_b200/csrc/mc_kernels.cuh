@@ -51,7 +51,7 @@ struct McEmitParams {
     const unsigned* counts;        // per chunk packed counts
     const uint4* base;             // per chunk exclusive prefix: x = records, y = verts, z = tris
     const McRecord* recs;
-    const uint4* masks;            // per active chunk: 128-bit activity mask (4 ballots)
+    const uint4* masks;            // per active chunk: 128-bit activity mask, bit q <-> cell q of the chunk
     unsigned rec_begin, rec_end;   // records emitted by this slab (owned layers)
     unsigned vlocal0, tlocal0;     // slab-local prefix at the first owned layer
     long long vglobal0, tglobal0;  // global ids of the slab's first owned vertex / triangle
@@ -72,10 +72,10 @@ struct McEmitParams {
 
 // host-side launchers (mc_kernels.cu)
 cudaError_t mc_init_tables();
-cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, cudaStream_t s);
+cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
                            McTotals* totals, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
-                              McRecord* recs, uint4* masks, cudaStream_t s);
+                              McRecord* recs, const uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);
