@@ -62,6 +62,11 @@ int sdfk_ctx_elapsed(sdfk_ctx* ctx, int slot_a, int slot_b, float* milliseconds)
 /* how many kernels this ctx has launched so far */
 int sdfk_ctx_launch_count(sdfk_ctx* ctx, int64_t* launches);
 
+/* page-locked host buffers: results exported into them travel at full PCIe speed (a pageable destination is staged
+ * by the driver at a fraction of it).  Optional -- every export accepts any host pointer. */
+int sdfk_host_alloc(size_t bytes, void** out);
+int sdfk_host_free(void* p);
+
 /* ---- SdfExpr.ToSdf(): SdfExprCompiler.Compile (SdfExpr.cs:208-211,234-271) ------------------------
  * body = statements of `sk_float4 sdf_eval(sk_float3 p)` in the SDF source dialect (csrc/sdfk_prelude.h),
  * produced by lowering the expression tree.  NVRTC-compiled for sm_100a without FMA contraction.       */

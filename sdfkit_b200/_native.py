@@ -27,6 +27,8 @@ SIGNATURES = {
     "sdfk_ctx_mark": (C.c_int, [_vp, C.c_int]),
     "sdfk_ctx_elapsed": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     "sdfk_ctx_launch_count": (C.c_int, [_vp, _i64p]),
+    "sdfk_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "sdfk_host_free": (C.c_int, [_vp]),
     "sdfk_sdf_compile": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
     "sdfk_sdf_destroy": (C.c_int, [_vp]),
     "sdfk_sdf_check": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -98,6 +100,40 @@ def fptr(a):
 def f32c(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a if shape is None else a.reshape(shape)
+
+
+class PinnedPool:
+    """Page-locked host buffers for exports (sdfk_host_alloc), recycled when every numpy view of a buffer has been
+    garbage collected -- pinning 100s of MB costs far more than copying them, so buffers are never freed eagerly."""
+    _free = {}      # size class -> [pointer, ...]
+
+    class _Block:
+        def __init__(self, ptr, size):
+            self.ptr, self.size = ptr, size
+
+        def __del__(self):
+            try:
+                PinnedPool._free.setdefault(self.size, []).append(self.ptr)
+            except Exception:
+                pass
+
+    @classmethod
+    def empty(cls, shape, dtype):
+        """A numpy array of `shape`/`dtype` living in pinned memory."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        size = 1 << max(12, (max(nbytes, 1) - 1).bit_length())
+        lst = cls._free.get(size)
+        if lst:
+            ptr = lst.pop()
+        else:
+            p = _vp()
+            check(lib().sdfk_host_alloc(size, C.byref(p)))
+            ptr = p.value
+        block = cls._Block(ptr, size)
+        buf = (C.c_ubyte * size).from_address(ptr)
+        buf._block = block                       # the ctypes buffer keeps the block alive; numpy keeps the buffer alive
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Context:

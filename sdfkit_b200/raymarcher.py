@@ -88,7 +88,7 @@ class RayMarcher:
         """RayMarcher.Render (RayMarcher.cs:45-64) -> Vec3Data; optional row band for sharded renders."""
         row_end = self.height if row_end is None else row_end
         cam, ivp = self.camera()
-        out = np.empty((row_end - row_begin, self.width, 3), dtype=np.float32)
+        out = N.PinnedPool.empty((row_end - row_begin, self.width, 3), np.float32)     # page-locked, recycled
         N.check(N.lib().sdfk_render(self.sdf.ctx.handle, self.sdf.handle, self.width, self.height, N.fptr(cam), N.fptr(ivp),
                                     float(self.NearPlaneDistance), float(self.FarPlaneDistance), int(self.DepthIterations),
                                     int(row_begin), int(row_end), N.fptr(out)))
@@ -98,7 +98,7 @@ class RayMarcher:
         """RayMarcher.RenderDepth (RayMarcher.cs:69-93) -> FloatData."""
         row_end = self.height if row_end is None else row_end
         cam, ivp = self.camera()
-        out = np.empty((row_end - row_begin, self.width), dtype=np.float32)
+        out = N.PinnedPool.empty((row_end - row_begin, self.width), np.float32)
         N.check(N.lib().sdfk_render_depth(self.sdf.ctx.handle, self.sdf.handle, self.width, self.height, N.fptr(cam),
                                           N.fptr(ivp), float(self.NearPlaneDistance), int(self.DepthIterations),
                                           int(row_begin), int(row_end), N.fptr(out)))

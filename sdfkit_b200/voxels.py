@@ -81,12 +81,14 @@ class GpuMesh:
         return {"classify_ms": s[0], "scan_ms": s[1], "compact_ms": s[2], "emit_ms": s[3],
                 "active_cells": int(s[4]), "records": int(s[5]), "chunks": int(s[6])}
 
-    def download(self):
+    def download(self, pinned=True):
+        """Copy the mesh to host memory (page-locked, recycled buffers by default: full PCIe speed)."""
         nv, nt = self.counts()
-        v = np.empty((nv, 3), dtype=np.float32)
-        c = np.empty((nv, 3), dtype=np.float32)
-        n = np.empty((nv, 3), dtype=np.float32)
-        t = np.empty(nt * 3, dtype=np.int32)
+        alloc = N.PinnedPool.empty if pinned else np.empty
+        v = alloc((nv, 3), np.float32)
+        c = alloc((nv, 3), np.float32)
+        n = alloc((nv, 3), np.float32)
+        t = alloc((nt * 3,), np.int32)
         aabb = np.zeros(6, dtype=np.float32)
         N.check(N.lib().sdfk_mesh_export(self.handle, N.fptr(v), N.fptr(c), N.fptr(n),
                                          t.ctypes.data_as(C.POINTER(C.c_int32)), N.fptr(aabb)))
