@@ -132,6 +132,9 @@ def run_reference(args):
 
 def run_ours(args):
     import numpy as np
+    # stdout carries exactly one JSON line: library chatter (e.g. NCCL's version banner) is sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -151,9 +154,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     sdf = sk.GpuSdf(expr, ctx=ctx)
     jit_s = time.perf_counter() - t0
-    ncz = skd.cells_along(n, 1)
-    kb, ke = skd.partition(ncz, world)[rank]
-    slab = skd.SlabMesher(sdf, mn, mx, n, n, n, kb, ke, clip=True)
+    spr = args.slabs_per_rank or 1
+    job = skd.ShardedMesher(sdf, mn, mx, n, n, n, rank, world, spr, clip=True, balanced=(world > 1 and not args.uniform_slabs))
     dev = torch.device("cuda", local)
 
     def barrier():
@@ -162,14 +164,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step():
-        slab.sample()
-        nv, nt = slab.classify()
-        if world > 1:
-            excl, tot = skd.all_gather_counts(nv, nt, device=dev)
-            vb, tb = excl[rank]
-        else:
-            vb, tb, tot = 0, 0, (nv, nt)
-        slab.emit(vb, tb)
+        counts = job.sample_classify()
+        allc = skd.all_gather_int64(counts, device=dev) if world > 1 else counts[None]
+        offs, tot = job.offsets(allc)
+        job.emit(offs)
         return tot
 
     for _ in range(max(args.warmup, 3)):
@@ -186,24 +184,26 @@ def run_ours(args):
     w0 = time.perf_counter()
     for _ in range(args.steps):
         h0 = time.perf_counter()
-        ctx.mark(2)
-        slab.sample()
-        ctx.mark(3)
-        nv, nt = slab.classify()
+        counts = np.zeros((spr, 2), dtype=np.int64)
+        k1 = 0.0
+        for k, s_ in enumerate(job.slabs):
+            if s_.ke > s_.kb:
+                ctx.mark(2)
+                s_.sample()
+                ctx.mark(3)
+                counts[k] = s_.classify()                     # synchronises: the event pair is complete
+                k1 += ctx.elapsed(2, 3)
         h1 = time.perf_counter()
-        if world > 1:
-            excl, tot = skd.all_gather_counts(nv, nt, device=dev)
-            vb, tb = excl[rank]
-        else:
-            vb, tb, tot = 0, 0, (nv, nt)
+        allc = skd.all_gather_int64(counts, device=dev) if world > 1 else counts[None]
+        offs, tot = job.offsets(allc)
         h2 = time.perf_counter()
-        slab.emit(vb, tb)
+        job.emit(offs)
         h3 = time.perf_counter()
         host["sample_classify"] += (h1 - h0) * 1e3
         host["allgather"] += (h2 - h1) * 1e3
         host["emit"] += (h3 - h2) * 1e3
-        sample_ms.append(ctx.elapsed(2, 3))
-        st = slab.mesh.stats()
+        sample_ms.append(k1)
+        st = job.stats()
         for k in stage:
             stage[k].append(st[k])
     ctx.mark(1)
@@ -223,7 +223,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (K1 sdfk_k_sample): 16 algorithmic bytes written per voxel, 0 read
     hbm, peak_src = peaks()
-    slab_vox = n * n * (slab.z1 - slab.z0)                     # voxels one launch writes on this rank (incl. halo slices)
+    slab_vox = sum(n * n * (s_.z1 - s_.z0) for s_ in job.slabs if s_.ke > s_.kb)   # voxels this rank's K1 launches write per step (incl. halo slices)
     k1_ms = statistics.mean(sample_ms)
     achieved = 16.0 * slab_vox / (k1_ms * 1e-3) / 1e9
     mesh_ms = {k: statistics.mean(v) for k, v in stage.items()}
@@ -261,7 +261,7 @@ def run_ours(args):
         else:
             def e2e_step():
                 tot_ = step()
-                parts = skd.mesh_device_tensors(slab.mesh, dev)
+                parts = [torch.cat(ps) for ps in zip(*[skd.mesh_device_tensors(s_.mesh, dev) for s_ in job.slabs if s_.mesh is not None])]
                 cnt = torch.tensor([parts[0].shape[0], parts[3].shape[0]], dtype=torch.int64, device=dev)
                 allc = torch.empty(world * 2, dtype=torch.int64, device=dev)
                 dist.all_gather_into_tensor(allc, cnt)
@@ -302,13 +302,13 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "README RepeatXY scene (%s): SdfExpr -> %d^3 Voxels (clip) + MarchingCubes, z-slab sharded over %d GPU(s)" % (args.scene, n, world),
-                       "grid": [n, n, n], "sdf_nodes": sdf.lowered.node_count, "sdf_flops_per_sample": sdf.lowered.flops,
+                       "grid": [n, n, n], "slabs_per_rank": spr, "slab_layers": [list(l) for l in job.layers], "sdf_nodes": sdf.lowered.node_count, "sdf_flops_per_sample": sdf.lowered.flops,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (16.0 * slab_vox / 1e9),
                        "parity_mode": "IEEE f32/f64, no FMA contraction (bit-exact vs the CPU oracle)"},
             "tris_per_s": ntris_total / (ms_per_step * 1e-3), "triangles": ntris_total, "vertices": int(tot[0]),
             "stages_ms": dict(sample_ms=k1_ms, **mesh_ms),
             "mesh": {"tris_per_s": ntris_total / max(mesh_total_ms * 1e-3, 1e-9), "cells_per_s": cells / max(mesh_total_ms * 1e-3, 1e-9),
-                     "classify_gbs_rank0": 4.0 * n * n * (slab.z1 - slab.z0) / (mesh_ms["classify_ms"] * 1e-3) / 1e9,
+                     "classify_gbs_rank0": 4.0 * slab_vox / (mesh_ms["classify_ms"] * 1e-3) / 1e9,
                      "note": "meshing stages only (K2-K4), slowest rank"},
             "per_rank_ms": rank_stages,
             "roofline": {"kernel": "sdfk_k_sample", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -317,8 +317,11 @@ def run_ours(args):
             "wall_ms_per_step": wall_ms / args.steps, "jit_compile_s": jit_s, "gpu_launches": int(launches),
             "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
-    slab.close()
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    job.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -333,6 +336,8 @@ def main():
     ap.add_argument("--grid", dest="n", type=int, default=0, help="grid size override (default: 1024 per GPU-equivalent)")
     ap.add_argument("--scene", default="readme")
     ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU-baseline sample")
+    ap.add_argument("--slabs-per-rank", type=int, default=0, help="z-slabs dealt round-robin to every rank (default 1)")
+    ap.add_argument("--uniform-slabs", action="store_true", help="equal-thickness z-slabs instead of the cost-balanced plan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -320,3 +320,56 @@ def test_layer_ranges_on_white_noise(sk, oracle):
         parts.append(m.download())
     merged = dist.merge_meshes(parts)
     assert_mesh_equal(merged, om, "white noise layer ranges")
+
+
+def test_interleaved_slabs_equal_single_gpu(sk):
+    """Round-robin multi-slab sharding (dist.ShardedMesher, what bench.py runs on N > 2 GPUs), emulated in one process:
+    3 ranks x 2 slabs each must reproduce the single-GPU mesh exactly."""
+    from sdfkit_b200 import dist, scenes
+    expr, mn, mx = scenes.readme_scene()
+    sdf = expr.ToSdf()
+    n, world, spr = 80, 3, 2
+    whole = sdf.ToMesh(mn, mx, n, n, n)
+    jobs = [dist.ShardedMesher(sdf, mn, mx, n, n, n, r, world, spr) for r in range(world)]
+    counts = np.stack([j.sample_classify() for j in jobs])          # what the all-gather delivers to every rank
+    parts = {}
+    for j in jobs:
+        offs, tot = j.offsets(counts)
+        j.emit(offs)
+        assert tuple(tot) == (len(whole.Vertices), len(whole.Triangles) // 3)
+        for g, s in zip(j.slab_ids, j.slabs):
+            parts[g] = s.mesh.download()
+    merged = dist.merge_meshes([parts[g] for g in sorted(parts)])
+    assert np.array_equal(merged.Triangles, whole.Triangles)
+    assert_bits_equal(merged.Vertices, whole.Vertices, "interleaved slab vertices")
+    assert_bits_equal(merged.Normals, whole.Normals, "interleaved slab normals")
+    assert_bits_equal(merged.Colors, whole.Colors, "interleaved slab colours")
+    for j in jobs:
+        j.close()
+
+
+def test_cost_balanced_slabs_equal_single_gpu(sk):
+    """The cost-balanced partition (dist.plan_layers) only moves the cuts: the merged mesh must not change, and the
+    slabs that hold the surface must come out thinner than the empty ones."""
+    from sdfkit_b200 import dist, scenes
+    expr, mn, mx = scenes.readme_scene()
+    sdf = expr.ToSdf()
+    n, world = 96, 4
+    whole = sdf.ToMesh(mn, mx, n, n, n)
+    jobs = [dist.ShardedMesher(sdf, mn, mx, n, n, n, r, world, 1, balanced=True) for r in range(world)]
+    layers = jobs[0].layers
+    assert all(j.layers == layers for j in jobs) and layers[0][0] == 0 and layers[-1][1] == n - 1
+    thick = [b - a for a, b in layers]
+    assert min(thick[1:3]) < max(thick[0], thick[3])          # the spheres sit in the middle of z
+    counts = np.stack([j.sample_classify() for j in jobs])
+    parts = []
+    for j in jobs:
+        offs, _ = j.offsets(counts)
+        j.emit(offs)
+        parts.append(j.slabs[0].mesh.download())
+    merged = dist.merge_meshes(parts)
+    assert np.array_equal(merged.Triangles, whole.Triangles)
+    assert_bits_equal(merged.Vertices, whole.Vertices, "balanced slab vertices")
+    assert_bits_equal(merged.Normals, whole.Normals, "balanced slab normals")
+    for j in jobs:
+        j.close()

@@ -143,6 +143,22 @@ def test_sharding_arithmetic():
     assert dist.slab_slices(2, 4, 2, 12) == (2, 11)
     excl, tot = dist.exclusive_offsets([[10, 20], [0, 0], [5, 7]])
     assert excl.tolist() == [[0, 0], [10, 20], [10, 20]] and tot.tolist() == [15, 27]
+    # cost-balanced contiguous cuts
+    assert dist.weighted_partition([1] * 8, 4) == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    wp = dist.weighted_partition([1, 1, 1, 1, 10, 10, 1, 1, 1, 1], 3)
+    assert wp[0][0] == 0 and wp[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(wp, wp[1:])) and all(b > a for a, b in wp)
+    assert wp[1] in ((4, 5), (4, 6), (5, 6))          # the heavy layers get a thin slab
+    assert dist.weighted_partition([5, 5], 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    # round-robin slabs: slab g belongs to rank g % world; offsets follow the slab order g
+    class _J(dist.ShardedMesher):
+        def __init__(self, rank, world, spr):
+            self.rank, self.world, self.spr = rank, world, spr
+            self.slab_ids = [rank + world * s for s in range(spr)]
+    counts = np.arange(2 * 3 * 2).reshape(2, 3, 2)            # [world=2, spr=3, 2]; slab g=r+2s has counts[r, s]
+    offs, tot = _J(1, 2, 3).offsets(counts)
+    order = [counts[g % 2, g // 2] for g in range(6)]
+    cum = np.concatenate([[np.zeros(2, int)], np.cumsum(order, axis=0)[:-1]])
+    assert offs.tolist() == [cum[1].tolist(), cum[3].tolist(), cum[5].tolist()] and tot.tolist() == counts.reshape(-1, 2).sum(0).tolist()
 
 
 _GLOO_WORKER = r'''
@@ -155,6 +171,8 @@ rank = dist.get_rank()
 counts = [(7, 11), (3, 5)]
 excl, tot = skd.all_gather_counts(*counts[rank])
 assert excl.tolist() == [[0, 0], [7, 11]] and tot.tolist() == [10, 16], (excl, tot)
+allc = skd.all_gather_int64(np.array([[rank, 1], [10 + rank, 2]]))
+assert allc.tolist() == [[0, 1, 10, 2], [1, 1, 11, 2]], allc
 local = torch.arange(counts[rank][0] * 3, dtype=torch.float32).reshape(-1, 3) + 100 * rank
 out = skd.gather_rows(local, [c[0] for c in counts])
 if rank == 0:
