@@ -221,6 +221,14 @@ def run_ours(args):
     value = nvox_total / (ms_per_step * 1e-3)
     ntris_total = int(tot[1])
 
+    # dram__bytes_read + dram__bytes_write of one K1 launch from the committed ncu capture (same workload only)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+        if world == 1 and n == 1024 and args.scene == "readme":
+            traffic = float(tj["traffic_bytes"])
+    except Exception:
+        pass
     # ---- roofline of the dominant kernel (K1 sdfk_k_sample): 16 algorithmic bytes written per voxel, 0 read
     hbm, peak_src = peaks()
     slab_vox = sum(n * n * (s_.z1 - s_.z0) for s_ in job.slabs if s_.ke > s_.kb)   # voxels this rank's K1 launches write per step (incl. halo slices)
@@ -259,16 +267,25 @@ def run_ours(args):
             e_s = (time.perf_counter() - e0) / e_steps
             d2h = mesh.Vertices.nbytes * 3 + mesh.Triangles.nbytes + 24
         else:
+            pinned = {}
+
+            def to_host(name, t):
+                """device tensor -> recycled page-locked host tensor (grown on demand)"""
+                buf = pinned.get(name)
+                if buf is None or buf.numel() < t.numel():
+                    buf = pinned[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, pin_memory=True)
+                out = buf[:t.numel()].view(t.shape)
+                out.copy_(t, non_blocking=True)
+                return out
+
             def e2e_step():
-                tot_ = step()
+                step()
                 parts = [torch.cat(ps) for ps in zip(*[skd.mesh_device_tensors(s_.mesh, dev) for s_ in job.slabs if s_.mesh is not None])]
-                cnt = torch.tensor([parts[0].shape[0], parts[3].shape[0]], dtype=torch.int64, device=dev)
-                allc = torch.empty(world * 2, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(allc, cnt)
-                allc = allc.cpu().numpy().reshape(world, 2)
-                outs = [skd.gather_rows(p, allc[:, 1 if i == 3 else 0]) for i, p in enumerate(parts)]
+                cnt = skd.all_gather_int64([parts[0].shape[0], parts[3].shape[0]], device=dev)
+                outs = [skd.gather_rows(p, cnt[:, 1 if i == 3 else 0]) for i, p in enumerate(parts)]
                 if rank == 0:
-                    host = [o.cpu() for o in outs]
+                    host = [to_host(i, o) for i, o in enumerate(outs)]
+                    torch.cuda.synchronize()
                     return sum(h.numel() * h.element_size() for h in host)
                 return 0
             e2e_step()
@@ -312,7 +329,7 @@ def run_ours(args):
                      "note": "meshing stages only (K2-K4), slowest rank"},
             "per_rank_ms": rank_stages,
             "roofline": {"kernel": "sdfk_k_sample", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 16.0 * slab_vox, "launch_ms": k1_ms},
             "wall_ms_per_step": wall_ms / args.steps, "jit_compile_s": jit_s, "gpu_launches": int(launches),
             "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
