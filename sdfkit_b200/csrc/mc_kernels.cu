@@ -891,8 +891,8 @@ template <int E>
 __device__ static inline void mc_add_edge_gradients(const double* v, int times, McF3& n)
 {
     constexpr int I1 = mc_end1(E), I2 = mc_end2(E);
-    const double w1 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I1)]));
-    const double w2 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I2)]));
+    const double w1 = __drcp_rn(MC_EPS + fabs(v[mc_reorder(I1)]));   // == 1.0 / x, correctly rounded
+    const double w2 = __drcp_rn(MC_EPS + fabs(v[mc_reorder(I2)]));
     double ax, ay, az, bx, by, bz;
     mc_vg_row<I1>(v, ax, ay, az);
     mc_vg_row<I2>(v, bx, by, bz);
@@ -1011,8 +1011,8 @@ __device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const
     constexpr int dx1 = I1 & 1, dy1 = (I1 >> 1) & 1, dz1 = I1 >> 2, dx2 = I2 & 1, dy2 = (I2 >> 1) & 1, dz2 = I2 >> 2;
     const double stp = (double)g.step;
     const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;           // Cell.x/y/z are voxel coordinates
-    const double w1 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I1)]));
-    const double w2 = 1.0 / (MC_EPS + fabs(v[mc_reorder(I2)]));
+    const double w1 = __drcp_rn(MC_EPS + fabs(v[mc_reorder(I1)]));   // == 1.0 / x, correctly rounded
+    const double w2 = __drcp_rn(MC_EPS + fabs(v[mc_reorder(I2)]));
     double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
     fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
     fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
@@ -1052,7 +1052,7 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
     const int X0 = i * g.step, Y0 = j * g.step, Z0 = kg * g.step;
     double w[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) w[q] = 1.0 / (MC_EPS + fabs(v[q]));
+    for (int q = 0; q < 8; q++) w[q] = __drcp_rn(MC_EPS + fabs(v[q]));
     double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
     McF3 fc = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -1087,7 +1087,9 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
 
 #define MC_FOR_EDGES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11)
 
-__global__ void __launch_bounds__(MC_EMIT_THREADS)
+// latency-bound (dependent lookups): more resident warps beat fewer spills -- measured 1.15 ms at 92 registers / 5 CTAs,
+// 0.94 ms at 48 registers / 10 CTAs per SM (1024^3 README scene)
+__global__ void __launch_bounds__(MC_EMIT_THREADS, 10)
 mc_emit_kernel(const McEmitParams p)
 {
     __shared__ int s_vid[MC_EMIT_THREADS][13];
