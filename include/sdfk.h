@@ -85,6 +85,12 @@ int sdfk_voxels_sample(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const f
 /* one z-slab [z_begin, z_end) of the same nx*ny*nz grid (multi-GPU sharding; halo slices are resampled) */
 int sdfk_voxels_sample_slab(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const float max[3],
                             int nx, int ny, int nz, int clip, int z_begin, int z_end, sdfk_voxels** out);
+/* Distance-only voxels for meshing (SdfEx.ToMesh, Sdf.cs:59-63, where the caller never sees the voxels): 4 B/voxel
+ * instead of 16.  Values are identical to sdfk_voxels_sample_slab's; the colours marching cubes needs are evaluated at
+ * the created vertices by a second JIT kernel, with identical results.  `sdf` must stay alive while these voxels are
+ * meshed; exporting Colors from them is SDFK_ERR_UNSUPPORTED. */
+int sdfk_voxels_sample_distances(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const float max[3],
+                                 int nx, int ny, int nz, int clip, int z_begin, int z_end, sdfk_voxels** out);
 /* re-sample into an existing voxels object (same grid; no allocation) -- the steady-state hot call */
 int sdfk_voxels_resample(sdfk_voxels* vox, sdfk_sdf* sdf, int clip);
 /* new Voxels(values, colors, min, max) (Voxels.cs:23-35): host arrays in C# layout

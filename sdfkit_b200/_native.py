@@ -36,6 +36,8 @@ SIGNATURES = {
     "sdfk_voxels_sample": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "sdfk_voxels_sample_slab": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(_vp)]),
+    "sdfk_voxels_sample_distances": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(_vp)]),
     "sdfk_voxels_resample": (C.c_int, [_vp, _vp, C.c_int]),
     "sdfk_voxels_import": (C.c_int, [_vp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "sdfk_voxels_export": (C.c_int, [_vp, _fp, _fp]),

@@ -121,6 +121,137 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
     }
 }
 
+// Distance-only variant of K1 for Sdf.ToMesh (SdfKit/Sdf.cs:59-63), where the caller never sees the voxels: 4 B/voxel
+// instead of 16; the colours marching cubes needs (two corners per created vertex) are evaluated afterwards by
+// sdfk_k_vertex_colors.  Same traversal and arithmetic as sdfk_k_sample.
+extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
+sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    const bool vec = (P.nx & 3) == 0;
+    const size_t plane = (size_t)P.nx * (size_t)P.ny;
+
+    for (unsigned work = blockIdx.x * SDFK_SAMPLE_WARPS + warp; work < P.nwork; work += gridDim.x * SDFK_SAMPLE_WARPS) {
+        const unsigned seg = sdfk_div(work, P.div_ncol);
+        const unsigned col = work - seg * P.ncol;
+        const unsigned uy = sdfk_div(col, P.div_tpr);
+        const unsigned xc = col - uy * P.tiles_per_row;
+        const int iy = (int)uy;
+        const int zl0 = (int)(((long long)seg * P.nzl) / P.zsplit);
+        const int zl1 = (int)(((long long)(seg + 1) * P.nzl) / P.zsplit);
+        const int x0 = (int)(xc * 128u + lane * 4u);
+        const float fx0 = (float)x0;                               // exact; fx0 + k is exact below 2^24
+        const float py = P.m1 + (float)iy * P.dy;                  // p = min' + i*delta, one mul + one add (Voxels.cs:104-106)
+        const bool ywall = P.clip && (iy == 0 || iy == P.ny - 1);
+        float px[4];
+        bool xywall[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            px[k] = P.m0 + (fx0 + (float)k) * P.dx;
+            xywall[k] = ywall || (P.clip && (x0 + k == 0 || x0 + k == P.nx - 1));
+        }
+        size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
+
+        for (int zl = zl0; zl < zl1; zl++, vbase += plane) {
+            const int iz = zl + P.z_begin;
+            const float pz = P.m2 + (float)iz * P.dz;
+            const bool zwall = P.clip && (iz == 0 || iz == P.nz - 1);
+            float d[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const sk_float4 r = sdf_eval(sk_make3(px[k], py, pz));
+                d[k] = (zwall || xywall[k]) ? P.clip_value : r.w;
+            }
+            if (vec) {
+                if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (x0 + k < P.nx) {
+                        const size_t v = vbase + lane * 4u + k;
+                        dist[v] = d[k];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Deferred vertex colours for distance-only voxels.  recipes[t] = (cell, edge) that created vertex t; the colour is
+// recomputed exactly as Cell.AddFaceFromEdgeIndex / CalculateCenterVertex do (Cell.cs:313-357,501-549): corner colours
+// come from sdf_eval at the corner voxels' sample positions (the very values K1 would have stored), the weights
+// 1 / (1e-7 + |v - iso|) from the stored distances, in double, mixed exactly like the reference.
+struct sdfk_color_params {
+    float m0, m1, m2, dx, dy, dz;   // sample positions: p = m + i * d (as in K1)
+    float iso;
+    int nx, ny;                     // voxel grid (x, y)
+    int z0;                         // global z of the first local slice
+    int step;
+    int ncx, ncy;                   // cells per row / rows per layer
+    int k0;                         // global cell layer of local layer 0 of the cell ids
+};
+
+static __device__ __forceinline__ void sdfk_corner(const sdfk_color_params& P, const float* __restrict__ dist, int i, int j, int kg,
+                                                   int dxc, int dyc, int dzc, double& w, float& r, float& g, float& b)
+{
+    const int x = (i + dxc) * P.step, y = (j + dyc) * P.step, z = (kg + dzc) * P.step;
+    const float v = dist[((size_t)(z - P.z0) * P.ny + y) * (size_t)P.nx + x];
+    w = 1.0 / (0.0000001 + fabs((double)v - (double)P.iso));
+    const sk_float4 c = sdf_eval(sk_make3(P.m0 + (float)x * P.dx, P.m1 + (float)y * P.dy, P.m2 + (float)z * P.dz));
+    r = c.x; g = c.y; b = c.z;
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+sdfk_k_vertex_colors(const sdfk_color_params P, const uint2* __restrict__ recipes, const float* __restrict__ dist,
+                     float* __restrict__ cols, long long nverts)
+{
+    // end corners of edge e as (dx | dy << 1 | dz << 2), EDGETORELATIVEPOS{X,Y,Z} (Luts.cs:26-28)
+    const unsigned char end1[12] = {0, 1, 3, 2, 4, 5, 7, 6, 0, 1, 3, 2};
+    const unsigned char end2[12] = {1, 3, 2, 0, 5, 7, 6, 4, 4, 5, 7, 6};
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nverts; t += (long long)gridDim.x * blockDim.x) {
+        const uint2 rc = recipes[t];
+        const int i = (int)(rc.x % (unsigned)P.ncx);
+        const unsigned t2 = rc.x / (unsigned)P.ncx;
+        const int j = (int)(t2 % (unsigned)P.ncy);
+        const int kg = P.k0 + (int)(t2 / (unsigned)P.ncy);
+        float cr, cg, cb;
+        if (rc.y < 12u) {
+            const int a = end1[rc.y], c = end2[rc.y];
+            double w1, w2;
+            float r1, g1, b1, r2, g2, b2;
+            sdfk_corner(P, dist, i, j, kg, a & 1, (a >> 1) & 1, a >> 2, w1, r1, g1, b1);
+            sdfk_corner(P, dist, i, j, kg, c & 1, (c >> 1) & 1, c >> 2, w2, r2, g2, b2);
+            double ff = 0.0;
+            ff += w1;
+            ff += w2;
+            const float f1 = (float)w1, f2 = (float)w2;
+            cr = (float)((double)(r1 * f1 + r2 * f2) / ff);
+            cg = (float)((double)(g1 * f1 + g2 * f2) / ff);
+            cb = (float)((double)(b1 * f1 + b2 * f2) / ff);
+        } else {   // centre vertex: corners 0..7 in the reference's numbering
+            double ff = 0.0;
+            float fr = 0.f, fg = 0.f, fb = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                double w;
+                float r, g, b;
+                sdfk_corner(P, dist, i, j, kg, (0x66 >> q) & 1, (0xCC >> q) & 1, (0xF0 >> q) & 1, w, r, g, b);
+                ff += w;
+                const float wq = (float)w;
+                if (q == 0) { fr = r * wq; fg = g * wq; fb = b * wq; }
+                else { fr = fr + r * wq; fg = fg + g * wq; fb = fb + b * wq; }
+            }
+            cr = (float)((double)fr / ff);
+            cg = (float)((double)fg / ff);
+            cb = (float)((double)fb / ff);
+        }
+        cols[t * 3 + 0] = cr;
+        cols[t * 3 + 1] = cg;
+        cols[t * 3 + 2] = cb;
+    }
+}
+
 // K6: colorsAndDistances[i] = sdf(points[i])  (Sdf.cs:8).  xyz: n*3 floats, rgbd: n*4 floats.
 extern "C" __global__ void __launch_bounds__(256)
 sdfk_k_eval(const float* __restrict__ xyz, float* __restrict__ rgbd, long long n)

@@ -910,7 +910,8 @@ __device__ static inline unsigned mc_float_key(float f)   // monotonic float -> 
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ static inline void mc_store_vertex(const McEmitParams& p, long long slot, McF3 pos, McF3 col, McF3 nsum, unsigned* lo, unsigned* hi)
+__device__ static inline void mc_store_vertex(const McEmitParams& p, long long slot, McF3 pos, McF3 col, McF3 nsum, unsigned* lo, unsigned* hi,
+                                             unsigned cell, unsigned edge)
 {
     // Cell.NegativeNormals (Cell.cs:97-109): -Vector3.Normalize(sum)
     const float len = sqrtf((nsum.x * nsum.x + nsum.y * nsum.y) + nsum.z * nsum.z);
@@ -930,7 +931,8 @@ __device__ static inline void mc_store_vertex(const McEmitParams& p, long long s
     float* co = p.cols + slot * 3;
     float* no = p.nrms + slot * 3;
     vo[0] = pos.x; vo[1] = pos.y; vo[2] = pos.z;
-    co[0] = col.x; co[1] = col.y; co[2] = col.z;
+    if (p.rgb) { co[0] = col.x; co[1] = col.y; co[2] = col.z; }
+    else p.recipes[slot] = make_uint2(cell, edge);           // colours follow from sdfk_k_vertex_colors
     no[0] = n.x; no[1] = n.y; no[2] = n.z;
     // Mesh.Measure (Mesh.cs:30-45), reduced per thread -> per warp -> one atomic per warp
     lo[0] = min(lo[0], mc_float_key(pos.x)); lo[1] = min(lo[1], mc_float_key(pos.y)); lo[2] = min(lo[2], mc_float_key(pos.z));
@@ -1004,7 +1006,7 @@ __device__ static inline void mc_gather_from(const McEmitParams& p, int ci, int 
 // (X,Z) e3;  z: (X-1,Y-1) e10, (X,Y-1) e11, (X-1,Y) e9, (X,Y) e8.
 template <int E>
 __device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const double* v, int occ_self, int i, int j, int kg,
-                                                    long long slot, unsigned* lo, unsigned* hi)
+                                                    long long slot, unsigned* lo, unsigned* hi, unsigned cell)
 {
     const McGrid& g = p.g;
     constexpr int I1 = mc_end1(E), I2 = mc_end2(E);
@@ -1016,13 +1018,15 @@ __device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const
     double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
     fx += dx1 * w1; fy += dy1 * w1; fz += dz1 * w1; ff += w1;
     fx += dx2 * w2; fy += dy2 * w2; fz += dz2 * w2; ff += w2;
-    const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
-    const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
-    const float f1 = (float)w1, f2 = (float)w2;
-    const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
-    McF3 pos, col, nsum = {0.f, 0.f, 0.f};
+    McF3 pos, col = {0.f, 0.f, 0.f}, nsum = {0.f, 0.f, 0.f};
     pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
-    col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
+    if (p.rgb) {
+        const float* c1 = p.rgb + mc_vox(g, i, j, kg, dx1, dy1, dz1) * 3;
+        const float* c2 = p.rgb + mc_vox(g, i, j, kg, dx2, dy2, dz2) * 3;
+        const float f1 = (float)w1, f2 = (float)w2;
+        const McF3 cm = {__ldg(c1) * f1 + __ldg(c2) * f2, __ldg(c1 + 1) * f1 + __ldg(c2 + 1) * f2, __ldg(c1 + 2) * f1 + __ldg(c2 + 2) * f2};
+        col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
+    }
     constexpr int AXIS = (dx1 != dx2) ? 0 : ((dy1 != dy2) ? 1 : 2);
     const int X = i + (dx1 < dx2 ? dx1 : dx2), Y = j + (dy1 < dy2 ? dy1 : dy2), Z = kg + (dz1 < dz2 ? dz1 : dz2);
     // the creating cell is the first sharing cell in visiting order; it sees the edge as E
@@ -1040,12 +1044,12 @@ __device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const
         if (E == 11) { mc_gather_from<9>(p, X - 1, Y, Z, nsum); mc_gather_from<8>(p, X, Y, Z, nsum); }
         if (E == 9) { mc_gather_from<8>(p, X, Y, Z, nsum); }
     }
-    mc_store_vertex(p, slot, pos, col, nsum, lo, hi);
+    mc_store_vertex(p, slot, pos, col, nsum, lo, hi, cell, (unsigned)E);
 }
 
 // Cell.CalculateCenterVertex (Cell.cs:501-549) + its accumulated gradient
 __device__ static inline void mc_create_center_vertex(const McEmitParams& p, const double* v, int times, int i, int j, int kg,
-                                                      long long slot, unsigned* lo, unsigned* hi)
+                                                      long long slot, unsigned* lo, unsigned* hi, unsigned cell)
 {
     const McGrid& g = p.g;
     const double stp = (double)g.step;
@@ -1059,11 +1063,13 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
     for (int q = 0; q < 8; q++) {
         const int cdx = (0x66 >> q) & 1, cdy = (0xCC >> q) & 1, cdz = (0xF0 >> q) & 1;   // corner q -> (dx,dy,dz)
         fx += (double)cdx * w[q]; fy += (double)cdy * w[q]; fz += (double)cdz * w[q]; ff += w[q];
-        const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx, cdy, cdz) * 3;
-        const float wq = (float)w[q];
-        const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
-        if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
-        else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
+        if (p.rgb) {
+            const float* cp = p.rgb + mc_vox(g, i, j, kg, cdx, cdy, cdz) * 3;
+            const float wq = (float)w[q];
+            const float cx = __ldg(cp) * wq, cy = __ldg(cp + 1) * wq, cz = __ldg(cp + 2) * wq;
+            if (q == 0) { fc.x = cx; fc.y = cy; fc.z = cz; }
+            else { fc.x = fc.x + cx; fc.y = fc.y + cy; fc.z = fc.z + cz; }
+        }
     }
     McF3 pos, col, nsum = {0.f, 0.f, 0.f};
     pos.x = (float)(X0 + stp * fx / ff); pos.y = (float)(Y0 + stp * fy / ff); pos.z = (float)(Z0 + stp * fz / ff);
@@ -1082,7 +1088,7 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
     }
     const float gx = (float)gs[0], gy = (float)gs[1], gz = (float)gs[2];
     for (int t = 0; t < times; t++) { nsum.x = nsum.x + gx; nsum.y = nsum.y + gy; nsum.z = nsum.z + gz; }
-    mc_store_vertex(p, slot, pos, col, nsum, lo, hi);
+    mc_store_vertex(p, slot, pos, col, nsum, lo, hi, cell, 12u);
 }
 
 #define MC_FOR_EDGES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11)
@@ -1131,13 +1137,13 @@ mc_emit_kernel(const McEmitParams p)
         }
         // ---- vertices this cell creates; slot = id - vlocal0
         const unsigned mine = refd & owned;
-#define VERT(E) if ((mine >> E) & 1u) mc_create_edge_vertex<E>(p, v, (int)MC_AUX_OCC(rec.aux, E), i, j, kg, (long long)vid[E] - (long long)p.vlocal0, lo, hi);
+#define VERT(E) if ((mine >> E) & 1u) mc_create_edge_vertex<E>(p, v, (int)MC_AUX_OCC(rec.aux, E), i, j, kg, (long long)vid[E] - (long long)p.vlocal0, lo, hi, rec.cell);
         VERT(5) VERT(6) VERT(10)
         if (mine & 0x0B9Fu) {     // grid-boundary cells also create edges 0-4, 7-9, 11
             VERT(0) VERT(1) VERT(2) VERT(3) VERT(4) VERT(7) VERT(8) VERT(9) VERT(11)
         }
 #undef VERT
-        if ((mine >> 12) & 1u) mc_create_center_vertex(p, v, meta->occ[12], i, j, kg, (long long)vid[12] - (long long)p.vlocal0, lo, hi);
+        if ((mine >> 12) & 1u) mc_create_center_vertex(p, v, meta->occ[12], i, j, kg, (long long)vid[12] - (long long)p.vlocal0, lo, hi, rec.cell);
     }
     // AABB: warp min/max, then one atomic per warp and component
 #pragma unroll

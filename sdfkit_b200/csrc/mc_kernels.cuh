@@ -59,6 +59,7 @@ struct McEmitParams {
     float* cols;
     float* nrms;
     int* tris;
+    uint2* recipes;                // distance-only voxels (rgb == NULL): per vertex (cell, edge) for the deferred colours
     unsigned* aabb_keys;           // 6 ordered-uint keys: min xyz, max xyz
     int has_xf;
     float M[16];                   // Mesh.Transform matrix (row-major, row-vector convention)

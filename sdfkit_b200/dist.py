@@ -115,7 +115,8 @@ def exclusive_offsets(counts):
 class SlabMesher:
     """One rank's share of Sdf.ToMesh on an nx*ny*nz grid: cell layers [kb, ke)."""
 
-    def __init__(self, sdf, vmin, vmax, nx, ny, nz, kb, ke, clip=True, iso=0.0, step=1):
+    def __init__(self, sdf, vmin, vmax, nx, ny, nz, kb, ke, clip=True, iso=0.0, step=1, colors=True):
+        self.colors = bool(colors)      # False: distance-only voxels, vertex colours evaluated from the SDF (Sdf.ToMesh)
         self.sdf = require_gpu_sdf(sdf)
         self.ctx = self.sdf.ctx
         self.min, self.max = numerics.vec3(vmin), numerics.vec3(vmax)
@@ -133,8 +134,9 @@ class SlabMesher:
         if self.vox is None:
             h = C.c_void_p()
             nx, ny, nz = self.dims
-            N.check(L.sdfk_voxels_sample_slab(self.ctx.handle, self.sdf.handle, N.fptr(self.min), N.fptr(self.max), nx, ny, nz,
-                                              1 if self.clip else 0, self.z0, self.z1, C.byref(h)))
+            fn = L.sdfk_voxels_sample_slab if self.colors else L.sdfk_voxels_sample_distances
+            N.check(fn(self.ctx.handle, self.sdf.handle, N.fptr(self.min), N.fptr(self.max), nx, ny, nz,
+                       1 if self.clip else 0, self.z0, self.z1, C.byref(h)))
             self.vox = h
         else:
             N.check(L.sdfk_voxels_resample(self.vox, self.sdf.handle, 1 if self.clip else 0))
@@ -210,7 +212,8 @@ class ShardedMesher:
     layers (the README scene fills 18 % of z) is spread over all ranks instead of landing on one or two, at the price
     of one extra halo per slab.  Global ids stay layer-major: offsets are exclusive sums over the slabs in order g."""
 
-    def __init__(self, sdf, vmin, vmax, nx, ny, nz, rank, world, slabs_per_rank=1, clip=True, iso=0.0, step=1, balanced=False):
+    def __init__(self, sdf, vmin, vmax, nx, ny, nz, rank, world, slabs_per_rank=1, clip=True, iso=0.0, step=1, balanced=False,
+                 colors=True):
         self.rank, self.world, self.spr = int(rank), int(world), int(slabs_per_rank)
         if balanced:
             layers = plan_layers(sdf, vmin, vmax, nx, ny, nz, self.world * self.spr, step, clip)
@@ -218,7 +221,7 @@ class ShardedMesher:
             layers = partition(cells_along(nz, step), self.world * self.spr)
         self.layers = layers
         self.slab_ids = [self.rank + self.world * s for s in range(self.spr)]
-        self.slabs = [SlabMesher(sdf, vmin, vmax, nx, ny, nz, layers[g][0], layers[g][1], clip, iso, step) for g in self.slab_ids]
+        self.slabs = [SlabMesher(sdf, vmin, vmax, nx, ny, nz, layers[g][0], layers[g][1], clip, iso, step, colors) for g in self.slab_ids]
 
     def sample_classify(self):
         """K1 + K2..K4a on every local slab; returns int64[slabs_per_rank, 2] (vertices, triangles)."""

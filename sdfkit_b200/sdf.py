@@ -34,6 +34,7 @@ class GpuSdf:
 
     def __init__(self, expr, ctx=None):
         self.ctx = ctx or N.Context.default()
+        self.expr = expr
         self.lowered = lower(expr)
         body = self.lowered.body.encode()
         h = C.c_void_p()
@@ -62,7 +63,10 @@ class GpuSdf:
 
     def ToMesh(self, min, max, nx, ny, nz, batchSize=SdfConfig.DefaultBatchSize, maxDegreeOfParallelism=-1,
                clipToBounds=True, isoValue=0.0, step=1, progress=None):
-        voxels = self.ToVoxels(min, max, nx, ny, nz, batchSize, maxDegreeOfParallelism, clipToBounds)
+        """SdfEx.ToMesh (Sdf.cs:59-63).  The caller never sees the voxels, so only distances are sampled (4 B/voxel
+        instead of 16) and the colours of the created vertices are evaluated from the SDF afterwards -- same mesh."""
+        from .voxels import Voxels
+        voxels = Voxels._sample(self, min, max, nx, ny, nz, clip=clipToBounds, colors=False)
         try:
             return voxels.ToMesh(isoValue, step, progress)
         finally:
@@ -86,6 +90,12 @@ class GpuSdf:
         rm.FarPlaneDistance = farPlaneDistance
         rm.DepthIterations = depthIterations
         return rm.Render()
+
+    def WithColor(self, red, green=None, blue=None):
+        """SdfEx.WithColor (Sdf.cs:101-115).  The reference wraps the delegate in an opaque lambda that overwrites the
+        colour; here the same effect is obtained on the expression tree (`expr.Color(c)`), which keeps the result on the
+        GPU path."""
+        return GpuSdf(self.expr.Color(red, green, blue), ctx=self.ctx)
 
     def Dispose(self):
         if self.handle:

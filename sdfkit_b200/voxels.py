@@ -151,13 +151,20 @@ class Voxels:
 
     # ---- sampling
     @classmethod
-    def _sample(cls, sdf, vmin, vmax, nx, ny, nz, clip):
+    def _sample(cls, sdf, vmin, vmax, nx, ny, nz, clip, colors=True):
+        """colors=False: distance-only voxels for meshing (4 B/voxel); vertex colours are evaluated from `sdf` when the
+        mesh is created, with identical results."""
         from .sdf import require_gpu_sdf
         sdf = require_gpu_sdf(sdf)
         v = cls(vmin, vmax, nx, ny, nz, ctx=sdf.ctx)
         h = C.c_void_p()
-        N.check(N.lib().sdfk_voxels_sample(sdf.ctx.handle, sdf.handle, N.fptr(v.Min), N.fptr(v.Max), v.NX, v.NY, v.NZ,
-                                           1 if clip else 0, C.byref(h)))
+        if colors:
+            N.check(N.lib().sdfk_voxels_sample(sdf.ctx.handle, sdf.handle, N.fptr(v.Min), N.fptr(v.Max), v.NX, v.NY, v.NZ,
+                                               1 if clip else 0, C.byref(h)))
+        else:
+            N.check(N.lib().sdfk_voxels_sample_distances(sdf.ctx.handle, sdf.handle, N.fptr(v.Min), N.fptr(v.Max), v.NX, v.NY,
+                                                         v.NZ, 1 if clip else 0, 0, v.NZ, C.byref(h)))
+            v._sdf = sdf                                   # keeps the SDF alive for the deferred colours
         v.handle = h
         return v
 
@@ -210,7 +217,14 @@ class Voxels:
         return self._colors
 
     def __getitem__(self, idx):
-        ix, iy, iz = idx
+        """voxels[ix, iy, iz] (Voxels.cs:42-46) or voxels[Vector3 p] -- the voxel containing point p (Voxels.cs:48-56)."""
+        if len(idx) == 3 and all(isinstance(k, (int, np.integer)) for k in idx):
+            ix, iy, iz = idx
+        else:
+            p = numerics.vec3(idx)
+            ix = int((p[0] - self.Min[0]) / self.DX)
+            iy = int((p[1] - self.Min[1]) / self.DY)
+            iz = int((p[2] - self.Min[2]) / self.DZ)
         return self.Values[ix, iy, iz]
 
     # ---- meshing

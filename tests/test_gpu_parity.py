@@ -373,3 +373,32 @@ def test_cost_balanced_slabs_equal_single_gpu(sk):
     assert_bits_equal(merged.Normals, whole.Normals, "balanced slab normals")
     for j in jobs:
         j.close()
+
+
+@pytest.mark.parametrize("name,dims,step", [("readme", (64, 64, 64), 1), ("perf", (50, 37, 29), 1), ("csg50", (96, 96, 48), 1),
+                                            ("readme", (72, 72, 72), 2)])
+def test_fused_to_mesh_equals_voxels_to_mesh(sk, oracle, name, dims, step):
+    """Sdf.ToMesh samples distances only and evaluates vertex colours from the SDF: the mesh must be
+    identical to the one made from fully materialised Voxels -- and to the oracle's."""
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    fused = sdf.ToMesh(mn, mx, nx, ny, nz, step=step)
+    full = sdf.ToVoxels(mn, mx, nx, ny, nz).ToMesh(step=step)
+    assert len(fused.Vertices) > 0
+    assert np.array_equal(fused.Triangles, full.Triangles)
+    assert_bits_equal(fused.Vertices, full.Vertices, "fused vertices")
+    assert_bits_equal(fused.Normals, full.Normals, "fused normals")
+    assert_bits_equal(fused.Colors, full.Colors, "fused colours")
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, threads=4)
+    om = oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx), step=step)
+    assert_mesh_equal(fused, om, "fused %s" % name)
+
+
+def test_distance_only_voxels_refuse_colors(sk):
+    from sdfkit_b200 import scenes
+    expr, mn, mx = scenes.readme_scene()
+    v = sk.Voxels._sample(expr.ToSdf(), mn, mx, 16, 16, 16, clip=True, colors=False)
+    assert v.Values.shape == (16, 16, 16)
+    with pytest.raises(sk.SdfkError, match="hold no colours"):
+        v.Colors
