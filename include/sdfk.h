@@ -61,6 +61,11 @@ int sdfk_ctx_mark(sdfk_ctx* ctx, int slot);
 int sdfk_ctx_elapsed(sdfk_ctx* ctx, int slot_a, int slot_b, float* milliseconds);
 /* how many kernels this ctx has launched so far */
 int sdfk_ctx_launch_count(sdfk_ctx* ctx, int64_t* launches);
+/* tuning switches (results never depend on them).  SDFK_OPT_SIGN_PLANES (default 1): the sampling kernels also write
+ * 1 sign bit per voxel (value > 0), from which marching cubes at iso 0 / step 1 finds the active cells without
+ * re-reading the distances; 0 = always classify from the distances. */
+#define SDFK_OPT_SIGN_PLANES 1
+int sdfk_ctx_set_option(sdfk_ctx* ctx, int option, int value);
 
 /* page-locked host buffers: results exported into them travel at full PCIe speed (a pageable destination is staged
  * by the driver at a fraction of it).  Optional -- every export accepts any host pointer. */
@@ -126,7 +131,7 @@ int sdfk_mesh_counts(sdfk_mesh* mesh, int64_t* nverts, int64_t* ntris);
 int sdfk_mesh_export(sdfk_mesh* mesh, float* vertices, float* colors, float* normals, int32_t* triangles,
                      float aabb[6]);
 int sdfk_mesh_device_ptrs(sdfk_mesh* mesh, void** vertices, void** colors, void** normals, void** triangles);
-/* stats[0..3] = device ms of classify, scan, compact, emit; stats[4] = active cells */
+/* stats[0..3] = device ms of classify, scan, compact, emit; stats[4] = active cells; stats[7] = 1 if classified from sign planes */
 int sdfk_mesh_stats(sdfk_mesh* mesh, double stats[8]);
 int sdfk_mesh_destroy(sdfk_mesh* mesh);
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sdfk_ctx_mark": (C.c_int, [_vp, C.c_int]),
     "sdfk_ctx_elapsed": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     "sdfk_ctx_launch_count": (C.c_int, [_vp, _i64p]),
+    "sdfk_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "sdfk_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "sdfk_host_free": (C.c_int, [_vp]),
     "sdfk_sdf_compile": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
@@ -138,6 +139,9 @@ class PinnedPool:
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
+OPT_SIGN_PLANES = 1
+
+
 class Context:
     """sdfk_ctx: one GPU + one stream.  `default()` gives the per-process context (LOCAL_RANK aware)."""
     _default = None
@@ -187,6 +191,9 @@ class Context:
         n = C.c_int64()
         check(lib().sdfk_ctx_launch_count(self.handle, C.byref(n)))
         return n.value
+
+    def set_option(self, option, value):
+        check(lib().sdfk_ctx_set_option(self.handle, int(option), int(value)))
 
     def close(self):
         if self.handle:

@@ -32,9 +32,40 @@ struct sdfk_sample_params {
     unsigned zsplit;           // z-segments per column (> 1 only when there are fewer columns than warps)
     unsigned nwork;            // ncol * zsplit
     sdfk_fastdiv div_tpr, div_ncol;
+    float sign_iso;            // iso value of the sign planes (see below)
 };
 
 #define SDFK_SAMPLE_WARPS 8
+
+// Sign blocks: a by-product of sampling that lets marching cubes find the active cells without re-reading the
+// distance field (1 bit per voxel instead of 4 bytes).  A warp walks its column (128 x of one y) in z, so every lane
+// keeps the signs of its 4 voxels over 8 consecutive z slices in ONE register and the warp stores 32 words = 128
+// contiguous bytes per 8 slices:  signs[((y*tiles_per_row + xc)*nzb + zl/8)*32 + L], bit 4*(zl%8) + k  <->  voxel
+// (xc*128 + 4L + k, y, zl) has value > iso (strict, Cell.cs:221-228; evaluated on the value actually stored, i.e.
+// after ClipToBounds).  nzb = ceil(nzl/8).  Bits of voxels beyond the row / slab are unspecified / zero; the consumer
+// (mc_classify_signs, mc_kernels.cu) masks the cells that do not exist.  z segments of a split column are 8-aligned,
+// so a word has exactly one writer.
+static __device__ __forceinline__ unsigned sdfk_gt_mask(float a, float b)   // 0xFFFFFFFF if a > b (false for NaN) else 0: one FSET
+{
+    unsigned m;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+    return m;
+}
+
+static __device__ __forceinline__ unsigned sdfk_sign_nibble(const float* d, float iso)
+{
+    const unsigned t1 = sdfk_gt_mask(d[1], iso) & 2u;
+    const unsigned t2 = (sdfk_gt_mask(d[0], iso) & 1u) | t1;
+    const unsigned t3 = (sdfk_gt_mask(d[2], iso) & 4u) | t2;
+    return (sdfk_gt_mask(d[3], iso) & 8u) | t3;
+}
+
+static __device__ __forceinline__ void sdfk_zsegment(const sdfk_sample_params& P, unsigned seg, int& zl0, int& zl1)
+{
+    const long long a = ((long long)seg * P.nzl) / P.zsplit, b = ((long long)(seg + 1) * P.nzl) / P.zsplit;
+    zl0 = seg == 0u ? 0 : min(P.nzl, (int)((a + 7) & ~7ll));
+    zl1 = seg + 1u == P.zsplit ? P.nzl : min(P.nzl, (int)((b + 7) & ~7ll));
+}
 
 // Device layout (DESIGN.md "data layout"): x fastest.  dist[(zl*ny + y)*nx + x], rgb[((zl*ny + y)*nx + x)*3 + c],
 // zl = z - z_begin.  A warp owns a COLUMN -- 128 consecutive x of one y -- and walks it in z: everything
@@ -46,7 +77,7 @@ struct sdfk_sample_params {
 // neighbouring columns, so at any moment the grid is writing a few contiguous planes.  Streaming
 // (evict-first) stores: the field is write-once.
 extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
-sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __restrict__ rgb)
+sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __restrict__ rgb, unsigned* __restrict__ signs)
 {
     __shared__ float4 stage[SDFK_SAMPLE_WARPS][96];
     const unsigned lane = threadIdx.x & 31u;
@@ -61,8 +92,8 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
         const unsigned uy = sdfk_div(col, P.div_tpr);
         const unsigned xc = col - uy * P.tiles_per_row;
         const int iy = (int)uy;
-        const int zl0 = (int)(((long long)seg * P.nzl) / P.zsplit);
-        const int zl1 = (int)(((long long)(seg + 1) * P.nzl) / P.zsplit);
+        int zl0, zl1;
+        sdfk_zsegment(P, seg, zl0, zl1);
         const int x0 = (int)(xc * 128u + lane * 4u);
         const float fx0 = (float)x0;                               // exact; fx0 + k is exact below 2^24
         const float py = P.m1 + (float)iy * P.dy;                  // p = min' + i*delta, one mul + one add (Voxels.cs:104-106)
@@ -77,8 +108,12 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
         const int nvalid = min(128, P.nx - (int)(xc * 128u));
         const int nq = (nvalid * 3) >> 2;                          // float4s of colour per tile on the vector path
         size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
+        unsigned* const scol = signs + ((size_t)uy * P.tiles_per_row + xc) * (size_t)((P.nzl + 7) >> 3) * 32u + lane;   // this lane's sign words
 
-        for (int zl = zl0; zl < zl1; zl++, vbase += plane) {
+        for (int zb0 = zl0; zb0 < zl1; zb0 += 8) {                  // zl0 is a multiple of 8: one sign word per lane and z-block
+        const int zend = min(zb0 + 8, zl1);
+        unsigned sacc = 0u, ssh = 0u;
+        for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
             const int iz = zl + P.z_begin;
             const float pz = P.m2 + (float)iz * P.dz;
             const bool zwall = P.clip && (iz == 0 || iz == P.nz - 1);
@@ -92,6 +127,9 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
                 c[3 * k + 1] = r.y;
                 c[3 * k + 2] = r.z;
             }
+#ifndef SDFK_X_NOSIGNS
+            sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
+#endif
             if (vec) {
                 if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
                 st[lane * 3 + 0] = make_float4(c[0], c[1], c[2], c[3]);
@@ -118,6 +156,8 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
                 }
             }
         }
+        if (signs) scol[(size_t)(zb0 >> 3) * 32u] = sacc;
+        }
     }
 }
 
@@ -125,7 +165,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
 // instead of 16; the colours marching cubes needs (two corners per created vertex) are evaluated afterwards by
 // sdfk_k_vertex_colors.  Same traversal and arithmetic as sdfk_k_sample.
 extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
-sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist)
+sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, unsigned* __restrict__ signs)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = threadIdx.x >> 5;
@@ -138,31 +178,43 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist)
         const unsigned uy = sdfk_div(col, P.div_tpr);
         const unsigned xc = col - uy * P.tiles_per_row;
         const int iy = (int)uy;
-        const int zl0 = (int)(((long long)seg * P.nzl) / P.zsplit);
-        const int zl1 = (int)(((long long)(seg + 1) * P.nzl) / P.zsplit);
+        int zl0, zl1;
+        sdfk_zsegment(P, seg, zl0, zl1);
         const int x0 = (int)(xc * 128u + lane * 4u);
         const float fx0 = (float)x0;                               // exact; fx0 + k is exact below 2^24
         const float py = P.m1 + (float)iy * P.dy;                  // p = min' + i*delta, one mul + one add (Voxels.cs:104-106)
-        const bool ywall = P.clip && (iy == 0 || iy == P.ny - 1);
+        // ClipToBounds without per-voxel branches: a wall row (y) or wall slice (z) skips the evaluation altogether, the two
+        // x walls are bit masks on the result: d = (d & keep) | setb
+        const bool rowwall = P.clip && (iy == 0 || iy == P.ny - 1);
         float px[4];
-        bool xywall[4];
+        unsigned keep[4], setb[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             px[k] = P.m0 + (fx0 + (float)k) * P.dx;
-            xywall[k] = ywall || (P.clip && (x0 + k == 0 || x0 + k == P.nx - 1));
+            const bool w = P.clip && (x0 + k == 0 || x0 + k == P.nx - 1);
+            keep[k] = w ? 0u : 0xFFFFFFFFu;
+            setb[k] = w ? __float_as_uint(P.clip_value) : 0u;
         }
         size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
+        unsigned* const scol = signs + ((size_t)uy * P.tiles_per_row + xc) * (size_t)((P.nzl + 7) >> 3) * 32u + lane;   // this lane's sign words
 
-        for (int zl = zl0; zl < zl1; zl++, vbase += plane) {
+        for (int zb0 = zl0; zb0 < zl1; zb0 += 8) {                  // zl0 is a multiple of 8: one sign word per lane and z-block
+        const int zend = min(zb0 + 8, zl1);
+        unsigned sacc = 0u, ssh = 0u;
+        for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
             const int iz = zl + P.z_begin;
-            const float pz = P.m2 + (float)iz * P.dz;
-            const bool zwall = P.clip && (iz == 0 || iz == P.nz - 1);
             float d[4];
+            if (rowwall || (P.clip && (iz == 0 || iz == P.nz - 1))) {      // warp-uniform
+                d[0] = d[1] = d[2] = d[3] = P.clip_value;
+            } else {
+                const float pz = P.m2 + (float)iz * P.dz;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const sk_float4 r = sdf_eval(sk_make3(px[k], py, pz));
-                d[k] = (zwall || xywall[k]) ? P.clip_value : r.w;
+                for (int k = 0; k < 4; k++)
+                    d[k] = __uint_as_float((__float_as_uint(sdf_eval(sk_make3(px[k], py, pz)).w) & keep[k]) | setb[k]);
             }
+#ifndef SDFK_X_NOSIGNS
+            sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
+#endif
             if (vec) {
                 if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
             } else {
@@ -174,6 +226,8 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist)
                     }
                 }
             }
+        }
+        if (signs) scol[(size_t)(zb0 >> 3) * 32u] = sacc;
         }
     }
 }

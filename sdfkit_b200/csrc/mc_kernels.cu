@@ -581,6 +581,111 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2' mc_classify_signs: the outputs of mc_classify (active cells + 128-bit activity mask per chunk) from the SIGN
+// BLOCKS the sampling kernels write as a by-product (csrc/jit_kernels.cuh) -- 1 bit per voxel instead of the 4-byte
+// distance, so the distance field is never re-read to find the surface.  step == 1 only (voxel tiles == cell chunks).
+// Layout: signs[((y*tpr + xc)*nzb + zb)*32 + L], bit 4p + k <-> voxel (xc*128 + 4L + k, y, 8*zb + p) has value > iso.
+// A warp takes one (row j, chunk xc) column and MC_SZB z-blocks (all loads issued up front): per block two coalesced 128-byte loads
+// (rows j, j+1) give every lane the signs of its 4 x 2 x 8 voxels; the x neighbour comes from lane L+1 (lane 31: the
+// next tile), the z neighbour from the next bit plane (plane 7: the next block).
+// ---------------------------------------------------------------------------------------------------
+#define MC_SZB 8
+
+__global__ void __launch_bounds__(256)
+mc_classify_signs_kernel(const McGrid g, const unsigned* __restrict__ signs, unsigned tpr, unsigned nzb, unsigned* __restrict__ counts,
+                         uint4* __restrict__ masks, unsigned ncols, unsigned nwork, int zb_first, int zb_last)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int off = g.k0 - g.z0;                                          // plane zl = local layer kl + off  (step == 1)
+    const size_t colwords = (size_t)nzb * 32u;
+    const unsigned sh = 4u * (lane & 7u);
+    for (unsigned w = gw; w < nwork; w += nw) {
+        const unsigned seg = w / ncols, col = w - seg * ncols;
+        const unsigned j = col / (unsigned)g.cpr, xc = col - j * (unsigned)g.cpr;
+        const int zb0 = zb_first + (int)(seg * MC_SZB);
+        const unsigned* rowA = signs + ((size_t)j * tpr + xc) * colwords + (size_t)zb0 * 32u + lane;
+        const unsigned* rowB = rowA + (size_t)tpr * colwords;
+        const bool edge = lane == 31u && xc + 1u < tpr;                   // lane 31's x neighbour: lane 0's word of the next tile
+        // cells of this lane that exist (i = xc*128 + 4L + k < ncx), replicated over the 8 planes
+        const int left = g.ncx - (int)(xc * 128u + lane * 4u);
+        const unsigned cellmask = (left >= 4 ? 15u : (left <= 0 ? 0u : ((1u << left) - 1u))) * 0x11111111u;
+        // all loads of the item first (blocks zb0 .. zb0 + MC_SZB, the last one only for its first plane)
+        unsigned a[MC_SZB + 1], b[MC_SZB + 1], an[MC_SZB + 1], bn[MC_SZB + 1];
+#pragma unroll
+        for (int q = 0; q <= MC_SZB; q++) {
+            const bool in = zb0 + q < (int)nzb;
+            a[q] = in ? __ldg(rowA + q * 32) : 0u;
+            b[q] = in ? __ldg(rowB + q * 32) : 0u;
+            an[q] = (in && edge) ? __ldg(rowA + q * 32 + colwords - 31) : 0u;
+            bn[q] = (in && edge) ? __ldg(rowB + q * 32 + colwords - 31) : 0u;
+        }
+        unsigned any[MC_SZB + 1], all[MC_SZB + 1];                        // OR / AND over rows j, j+1 and voxels c, c+1; bit 4p + k
+#pragma unroll
+        for (int q = 0; q <= MC_SZB; q++) {
+            const unsigned sa = __shfl_down_sync(FULL, a[q], 1), sb = __shfl_down_sync(FULL, b[q], 1);
+            const unsigned na = lane == 31u ? an[q] : sa, nb = lane == 31u ? bn[q] : sb;
+            const unsigned ax = ((a[q] >> 1) & 0x77777777u) | ((na << 3) & 0x88888888u);   // voxel c+1: k+1 of this lane, k = 0 of the next
+            const unsigned bx = ((b[q] >> 1) & 0x77777777u) | ((nb << 3) & 0x88888888u);
+            any[q] = a[q] | ax | b[q] | bx;
+            all[q] = a[q] & ax & b[q] & bx;
+        }
+#pragma unroll
+        for (int q = 0; q < MC_SZB; q++) {
+            const int zb = zb0 + q;
+            if (zb > zb_last) break;                                       // warp-uniform
+            const unsigned anyz = (any[q] >> 4) | (any[q + 1] << 28), allz = (all[q] >> 4) | (all[q + 1] << 28);
+            const unsigned act = (any[q] | anyz) & ~(all[q] & allz) & cellmask;   // bit 4p + k: cell (4L + k) of layer 8zb + p - off
+            const int kl_base = zb * 8 - off;
+            const int klane = kl_base + (int)lane;                         // lane p < 8 stores the count of layer p
+            const bool cnt_lane = lane < 8u && klane >= 0 && klane < g.nk;
+            unsigned* const cnt_out = counts + ((size_t)(cnt_lane ? klane : 0) * g.ncy + j) * g.cpr + xc;
+            if (!__any_sync(FULL, act != 0u)) {
+                if (cnt_lane) *cnt_out = 0u;
+                continue;
+            }
+            // active cells of all 8 layers at once: nibble-wise popcount, summed over the warp in byte fields (<= 128 each)
+            unsigned t = act - ((act >> 1) & 0x55555555u);
+            t = (t & 0x33333333u) + ((t >> 2) & 0x33333333u);                           // nibble p = active cells of layer p in this lane
+            const unsigned ce = __reduce_add_sync(FULL, t & 0x0F0F0F0Fu);               // byte q = layer 2q
+            const unsigned co = __reduce_add_sync(FULL, (t >> 4) & 0x0F0F0F0Fu);        // byte q = layer 2q + 1
+            if (cnt_lane) *cnt_out = (((lane & 1u) ? co : ce) >> (8u * ((lane >> 1) & 3u))) & 0xFFu;
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const int kl = kl_base + p;
+                const unsigned n = (((p & 1) ? co : ce) >> (8 * (p >> 1))) & 0xFFu;
+                if (n == 0u || kl < 0 || kl >= g.nk) continue;                          // warp-uniform
+                // the chunk's 128-bit activity mask in natural cell order (bit 4L + k): word w = OR of the nibbles of lanes 8w..8w+7
+                unsigned wd = ((act >> (4 * p)) & 15u) << sh;
+                wd |= __shfl_xor_sync(FULL, wd, 1);
+                wd |= __shfl_xor_sync(FULL, wd, 2);
+                wd |= __shfl_xor_sync(FULL, wd, 4);
+                if ((lane & 7u) == 0u) reinterpret_cast<unsigned*>(masks + ((size_t)kl * g.ncy + j) * g.cpr + xc)[lane >> 3] = wd;
+            }
+        }
+    }
+}
+
+cudaError_t mc_launch_classify_signs(const McGrid& g, const unsigned* signs, unsigned tiles_per_row, unsigned nzb, unsigned* counts,
+                                     uint4* masks, cudaStream_t s)
+{
+    if (g.nchunks == 0) return cudaSuccess;
+    if (g.step != 1 || g.k0 < g.z0) return cudaErrorInvalidValue;
+    const int off = g.k0 - g.z0;
+    const int zb_first = off >> 3, zb_last = (off + g.nk - 1) >> 3;        // z-blocks holding the lower plane of a classified layer
+    const unsigned ncols = (unsigned)g.ncy * (unsigned)g.cpr, nseg = (unsigned)(zb_last - zb_first + MC_SZB) / MC_SZB;
+    const unsigned long long nwork = (unsigned long long)ncols * nseg;   // <= nchunks < 2^32
+    if (nwork > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned long long blocks = (nwork + 7) / 8;
+    if (blocks > (unsigned long long)sms * 8u) blocks = (unsigned long long)sms * 8u;
+    mc_classify_signs_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, signs, tiles_per_row, nzb, counts, masks, ncols, (unsigned)nwork, zb_first, zb_last);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K3 mc_scan: exclusive prefix sums (records, vertices, triangles) over the chunk counts, in visiting
 // order.  Single pass: warp-shuffle scans inside a tile, decoupled look-back between tiles.
 // ---------------------------------------------------------------------------------------------------

@@ -74,6 +74,9 @@ struct McEmitParams {
 // host-side launchers (mc_kernels.cu)
 cudaError_t mc_init_tables();
 cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, uint4* masks, cudaStream_t s);
+// same outputs from the sign planes written by the sampling kernels (step == 1): no pass over the distance field
+cudaError_t mc_launch_classify_signs(const McGrid& g, const unsigned* signs, unsigned tiles_per_row, unsigned nzb, unsigned* counts,
+                                     uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
                            McTotals* totals, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);

@@ -79,7 +79,7 @@ class GpuMesh:
         s = (C.c_double * 8)()
         N.check(N.lib().sdfk_mesh_stats(self.handle, s))
         return {"classify_ms": s[0], "scan_ms": s[1], "compact_ms": s[2], "emit_ms": s[3],
-                "active_cells": int(s[4]), "records": int(s[5]), "chunks": int(s[6])}
+                "active_cells": int(s[4]), "records": int(s[5]), "chunks": int(s[6]), "from_signs": bool(s[7])}
 
     def download(self, pinned=True):
         """Copy the mesh to host memory (page-locked, recycled buffers by default: full PCIe speed)."""

@@ -402,3 +402,60 @@ def test_distance_only_voxels_refuse_colors(sk):
     assert v.Values.shape == (16, 16, 16)
     with pytest.raises(sk.SdfkError, match="hold no colours"):
         v.Colors
+
+
+# ---------------------------------------------------------------------------------------------- sign planes (K2')
+
+@pytest.mark.parametrize("name,dims,clip", [("readme", (64, 64, 64), True), ("perf", (50, 37, 29), True), ("readme", (260, 9, 7), True),
+                                            ("csg50", (129, 40, 33), False), ("readme", (257, 6, 5), True), ("sphere", (2, 2, 2), False),
+                                            ("readme", (128, 128, 20), True)])
+def test_sign_plane_classify_equals_distance_classify(sk, oracle, name, dims, clip):
+    """Marching cubes at iso 0 / step 1 finds the active cells from the sign planes the sampling kernel wrote (K2'); with the
+    option off it reads the distances (K2).  Both must give the oracle's mesh, for ragged rows (nx % 128 in {0, 1, 2, 4, ...})
+    and partial last tiles too."""
+    from sdfkit_b200 import _native as N
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    ctx = sdf.ctx
+    meshes = {}
+    try:
+        for opt in (1, 0):
+            ctx.set_option(N.OPT_SIGN_PLANES, opt)
+            vox = sdf.ToVoxels(mn, mx, nx, ny, nz, clipToBounds=clip)
+            gm = sk.MarchingCubes.CreateGpuMesh(vox)
+            assert gm.stats()["from_signs"] == bool(opt)
+            meshes[opt] = gm.download()
+            gm.destroy()
+            fused = sdf.ToMesh(mn, mx, nx, ny, nz, clipToBounds=clip)
+            assert np.array_equal(fused.Triangles, meshes[opt].Triangles)
+            assert_bits_equal(fused.Vertices, meshes[opt].Vertices, "fused vertices (sign planes %d)" % opt)
+    finally:
+        ctx.set_option(N.OPT_SIGN_PLANES, 1)
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, clip_to_bounds=clip, threads=4)
+    om = oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx))
+    for opt in (1, 0):
+        assert_mesh_equal(meshes[opt], om, "%s %s sign planes %d" % (name, dims, opt))
+
+
+def test_sign_planes_follow_the_stored_values(sk, oracle):
+    """The sign planes describe the values actually stored: a later ClipToBounds invalidates them (K2 takes over), another
+    iso value or step ignores them -- the mesh is the oracle's in every case."""
+    from sdfkit_b200 import scenes
+    expr, mn, mx = scenes.readme_scene()
+    sdf = expr.ToSdf()
+    n = 48
+    vox = sk.Voxels.SampleSdf(sdf, mn, mx, n, n, n)          # unclipped
+    vox.ClipToBounds()
+    gm = sk.MarchingCubes.CreateGpuMesh(vox)
+    assert gm.stats()["from_signs"] is False
+    m = gm.download()
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), n, n, n, clip_to_bounds=True, threads=4)
+    assert_mesh_equal(m, oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx)), "clip after sampling")
+    vox2 = sdf.ToVoxels(mn, mx, n, n, n)
+    for iso, step in ((0.125, 1), (0.0, 2)):
+        gm = sk.MarchingCubes.CreateGpuMesh(vox2, iso, step)
+        assert gm.stats()["from_signs"] is False
+        assert_mesh_equal(gm.download(), oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx), iso=iso, step=step), "iso %g step %d" % (iso, step))
+    gm = sk.MarchingCubes.CreateGpuMesh(vox2)
+    assert gm.stats()["from_signs"] is True
