@@ -126,6 +126,18 @@ int sdfk_mesh_classify(sdfk_ctx* ctx, sdfk_voxels* vox, float iso, int step, int
 int sdfk_mesh_emit(sdfk_mesh* mesh, int64_t vertex_base, int64_t triangle_base, const float transform[16],
                    const float normal_transform[16]);
 int sdfk_mesh_counts(sdfk_mesh* mesh, int64_t* nverts, int64_t* ntris);
+/* SdfEx.ToMesh (Sdf.cs:59-63) in one call, with the mesh delivered to HOST memory.  The grid is cut into z-slabs
+ * (nslabs; 0 = automatic: ~64 cell layers each, at most 16); each slab is sampled (distance-only voxels + sign blocks), classified,
+ * compacted and emitted at its global vertex / triangle offsets, and its part of the mesh streams to page-locked host
+ * memory on a copy stream while the following slabs are computed.  The result is identical, bit for bit and in order,
+ * to sdfk_voxels_sample + sdfk_mesh_create + sdfk_mesh_export.  The arrays live in page-locked memory owned by the mesh
+ * handle (recycled through the ctx) until sdfk_mesh_destroy; sdfk_mesh_export on such a mesh is a host memcpy.
+ * progress is called on the calling thread, per cell layer, as slabs complete. */
+int sdfk_sdf_to_mesh_host(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const float max[3], int nx, int ny, int nz, int clip,
+                          float iso, int step, const float transform[16], const float normal_transform[16], int nslabs,
+                          sdfk_progress_fn progress, void* user, sdfk_mesh** out);
+int sdfk_mesh_host_ptrs(sdfk_mesh* mesh, const float** vertices, const float** colors, const float** normals,
+                        const int32_t** triangles);
 /* Mesh.Vertices/Colors/Normals/Triangles + Min/Max (Mesh.cs:10-18): any pointer may be NULL.
  * aabb = {min.x, min.y, min.z, max.x, max.y, max.z}                                                     */
 int sdfk_mesh_export(sdfk_mesh* mesh, float* vertices, float* colors, float* normals, int32_t* triangles,

@@ -49,6 +49,9 @@ SIGNATURES = {
     "sdfk_mesh_classify": (C.c_int, [_vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _i64p, _i64p]),
     "sdfk_mesh_emit": (C.c_int, [_vp, C.c_int64, C.c_int64, _fp, _fp]),
     "sdfk_mesh_counts": (C.c_int, [_vp, _i64p, _i64p]),
+    "sdfk_sdf_to_mesh_host": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, C.c_int,
+                                        PROGRESS_FN, _vp, C.POINTER(_vp)]),
+    "sdfk_mesh_host_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "sdfk_mesh_export": (C.c_int, [_vp, _fp, _fp, _fp, C.POINTER(C.c_int32), _fp]),
     "sdfk_mesh_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "sdfk_mesh_stats": (C.c_int, [_vp, C.POINTER(C.c_double)]),

@@ -799,10 +799,9 @@ mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, un
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
                            McTotals* totals, cudaStream_t s)
 {
-    cudaError_t err = cudaMemsetAsync(totals, 0, sizeof(McTotals), s);
-    if (err != cudaSuccess || nchunks == 0) return err;
+    if (nchunks == 0) return cudaSuccess;                     // (the last tile always writes the totals otherwise)
     if (ws_bytes < mc_scan_workspace_bytes(nchunks)) return cudaErrorInvalidValue;
-    err = cudaMemsetAsync(scan_ws, 0, mc_scan_workspace_bytes(nchunks), s);
+    cudaError_t err = cudaMemsetAsync(scan_ws, 0, mc_scan_workspace_bytes(nchunks), s);
     if (err != cudaSuccess) return err;
     const unsigned ntiles = (nchunks + SCAN_TILE - 1) / SCAN_TILE;
     mc_scan_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(counts, base, nchunks, (ScanWs*)scan_ws, totals);
@@ -1266,5 +1265,22 @@ cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
     const unsigned n = p.rec_end - p.rec_begin;
     if (n == 0) return cudaSuccess;
     mc_emit_kernel<<<(n + MC_EMIT_THREADS - 1u) / MC_EMIT_THREADS, MC_EMIT_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A few words device -> mapped page-locked host memory, written by a kernel: the small read-backs between the stages
+// must not queue behind a large mesh download in the device-to-host copy engine (cudaMemcpyAsync would).
+// ---------------------------------------------------------------------------------------------------
+__global__ void mc_readback_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, unsigned nwords)
+{
+    for (unsigned k = threadIdx.x; k < nwords; k += blockDim.x) dst[k] = src[k];
+    __threadfence_system();
+}
+
+cudaError_t mc_launch_readback(const void* src_dev, void* dst_host_mapped, unsigned nwords, cudaStream_t s)
+{
+    if (nwords == 0) return cudaSuccess;
+    mc_readback_kernel<<<1, 32, 0, s>>>((const unsigned*)src_dev, (unsigned*)dst_host_mapped, nwords);
     return cudaGetLastError();
 }

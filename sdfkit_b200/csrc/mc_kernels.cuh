@@ -83,3 +83,5 @@ size_t mc_scan_workspace_bytes(unsigned nchunks);
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
                               McRecord* recs, const uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);
+// nwords 32-bit words from device memory to MAPPED page-locked host memory, by a kernel (no copy engine involved)
+cudaError_t mc_launch_readback(const void* src_dev, void* dst_host_mapped, unsigned nwords, cudaStream_t s);

@@ -62,15 +62,21 @@ class GpuSdf:
         return Voxels._sample(self, min, max, nx, ny, nz, clip=clipToBounds)
 
     def ToMesh(self, min, max, nx, ny, nz, batchSize=SdfConfig.DefaultBatchSize, maxDegreeOfParallelism=-1,
-               clipToBounds=True, isoValue=0.0, step=1, progress=None):
-        """SdfEx.ToMesh (Sdf.cs:59-63).  The caller never sees the voxels, so only distances are sampled (4 B/voxel
-        instead of 16) and the colours of the created vertices are evaluated from the SDF afterwards -- same mesh."""
-        from .voxels import Voxels
-        voxels = Voxels._sample(self, min, max, nx, ny, nz, clip=clipToBounds, colors=False)
-        try:
-            return voxels.ToMesh(isoValue, step, progress)
-        finally:
-            voxels.Dispose()
+               clipToBounds=True, isoValue=0.0, step=1, progress=None, slabs=0):
+        """SdfEx.ToMesh (Sdf.cs:59-63).  The caller never sees the voxels, so only distances are sampled (4 B/voxel instead
+        of 16) and the colours of the created vertices are evaluated from the SDF afterwards; the grid is processed in
+        z-slabs whose finished mesh parts stream to page-locked host memory while the next slabs are computed
+        (sdfk_sdf_to_mesh_host).  Same mesh, bit for bit, as ToVoxels(...).ToMesh(...)."""
+        from .voxels import GpuMesh
+        vmin, vmax = numerics.vec3(min), numerics.vec3(max)
+        M, Nm = numerics.mesh_transforms(vmin, vmax, int(nx), int(ny), int(nz))
+        M, Nm = N.f32c(M), N.f32c(Nm)
+        cb = N.PROGRESS_FN((lambda f, _u: progress(f)) if progress else (lambda f, _u: None))
+        h = C.c_void_p()
+        N.check(N.lib().sdfk_sdf_to_mesh_host(self.ctx.handle, self.handle, N.fptr(vmin), N.fptr(vmax), int(nx), int(ny), int(nz),
+                                              1 if clipToBounds else 0, float(isoValue), int(step), N.fptr(M), N.fptr(Nm), int(slabs),
+                                              cb if progress else C.cast(None, N.PROGRESS_FN), None, C.byref(h)))
+        return GpuMesh(h).host_view()
 
     def ToImage(self, width, height, *camera, verticalFieldOfViewDegrees=60.0, nearPlaneDistance=1.0,
                 farPlaneDistance=100.0, depthIterations=40, batchSize=SdfConfig.DefaultBatchSize,

@@ -94,6 +94,27 @@ class GpuMesh:
                                          t.ctypes.data_as(C.POINTER(C.c_int32)), N.fptr(aabb)))
         return Mesh(v, c, n, t, aabb[:3].copy(), aabb[3:].copy())
 
+    def host_view(self):
+        """Mesh over the page-locked host arrays of a mesh made by sdfk_sdf_to_mesh_host (zero copy).  The arrays keep
+        this handle alive; the buffers go back to the context's pool when the last of them is garbage collected."""
+        nv, nt = self.counts()
+        ptrs = [C.c_void_p() for _ in range(4)]
+        N.check(N.lib().sdfk_mesh_host_ptrs(self.handle, *[C.byref(p) for p in ptrs]))
+        aabb = np.zeros(6, dtype=np.float32)
+        N.check(N.lib().sdfk_mesh_export(self.handle, None, None, None, None, N.fptr(aabb)))
+
+        def view(ptr, rows, dtype, shape):
+            if rows == 0 or not ptr.value:
+                return np.zeros(shape, dtype=dtype)
+            buf = (C.c_ubyte * (rows * 12)).from_address(ptr.value)
+            buf._owner = self                      # numpy keeps the ctypes buffer alive, which keeps the mesh handle alive
+            return np.frombuffer(buf, dtype=dtype).reshape(shape)
+        v = view(ptrs[0], nv, np.float32, (nv, 3))
+        c = view(ptrs[1], nv, np.float32, (nv, 3))
+        n = view(ptrs[2], nv, np.float32, (nv, 3))
+        t = view(ptrs[3], nt, np.int32, (nt * 3,))
+        return Mesh(v, c, n, t, aabb[:3].copy(), aabb[3:].copy())
+
     def destroy(self):
         if self.handle:
             N.lib().sdfk_mesh_destroy(self.handle)

@@ -459,3 +459,42 @@ def test_sign_planes_follow_the_stored_values(sk, oracle):
         assert_mesh_equal(gm.download(), oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx), iso=iso, step=step), "iso %g step %d" % (iso, step))
     gm = sk.MarchingCubes.CreateGpuMesh(vox2)
     assert gm.stats()["from_signs"] is True
+
+
+# ---------------------------------------------------------------------------------------------- pipelined Sdf.ToMesh
+
+@pytest.mark.parametrize("name,dims,slabs,step,iso", [
+    ("readme", (64, 64, 64), 1, 1, 0.0), ("readme", (64, 64, 64), 2, 1, 0.0), ("readme", (64, 64, 64), 5, 1, 0.0),
+    ("readme", (64, 64, 64), 63, 1, 0.0), ("perf", (50, 37, 29), 3, 1, 0.0), ("csg50", (96, 96, 48), 4, 1, 0.0),
+    ("readme", (72, 72, 72), 3, 2, 0.0), ("readme", (64, 64, 64), 4, 1, 0.125), ("sphere", (2, 2, 2), 0, 1, 0.0),
+    ("sphere", (1, 1, 1), 0, 1, 0.0), ("readme", (260, 40, 300), 0, 1, 0.0)])
+def test_pipelined_to_mesh_host(sk, oracle, name, dims, slabs, step, iso):
+    """Sdf.ToMesh = sdfk_sdf_to_mesh_host: z-slabs software-pipelined on the device, mesh parts streamed to page-locked host
+    memory.  Any slab count must give the oracle's mesh, bit for bit and in the reference's order."""
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    seen = []
+    mesh = sdf.ToMesh(mn, mx, nx, ny, nz, isoValue=iso, step=step, slabs=slabs, progress=seen.append)
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, threads=4)
+    oseen = []
+    om = oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx), iso=iso, step=step, progress=oseen.append)
+    assert_mesh_equal(mesh, om, "pipelined %s %s slabs=%d" % (name, dims, slabs))
+    assert np.array_equal(np.float32(seen), np.float32(oseen), equal_nan=True)   # IProgress<float> reports (MarchingCubes.cs:81); 0/0 on a 2^3 grid
+
+
+def test_pipelined_to_mesh_buffers_are_recycled_safely(sk):
+    """The page-locked arrays belong to the mesh: a second ToMesh must not overwrite the first one's data while it is alive."""
+    from sdfkit_b200 import scenes
+    e1, mn, mx = scenes.readme_scene()
+    e2, mn2, mx2 = scenes.sphere()
+    s1, s2 = e1.ToSdf(), e2.ToSdf()
+    a = s1.ToMesh(mn, mx, 64, 64, 64)
+    va, ta = a.Vertices.copy(), a.Triangles.copy()
+    b = s2.ToMesh(mn2, mx2, 64, 64, 64)
+    assert np.array_equal(a.Vertices, va) and np.array_equal(a.Triangles, ta)
+    assert len(b.Vertices) == 4872 and len(b.Triangles) == 3 * 9740          # BASELINE config 1 counts
+    del a
+    c = s1.ToMesh(mn, mx, 64, 64, 64)                                        # reuses a's buffers
+    assert np.array_equal(c.Vertices, va) and np.array_equal(c.Triangles, ta)
+    assert len(b.Vertices) == 4872
