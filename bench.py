@@ -211,7 +211,6 @@ def run_ours(args):
     wall = time.perf_counter() - w0
     dev_ms = ctx.elapsed(0, 1)
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,9 +326,11 @@ def run_ours(args):
         e_s = te.item()
         e2e = {"value": nvox_total / e_s, "unit": UNIT, "ms_per_step": e_s * 1e3, "h2d_bytes_per_step": 256,
                "d2h_bytes_per_step": int(d2h),
-               "note": "Sdf.ToMesh through the host API; the SDF is analytic so the only host->device bytes are kernel "
-                       "parameters; the mesh (vertices, colours, normals, triangles) is copied to host memory every step"}
+               "note": "Sdf.ToMesh through the host API (sdfk_sdf_to_mesh_host: z-slabs pipelined, mesh parts streamed to page-locked "
+                       "host memory while the next slabs are computed); the SDF is analytic so the only host->device bytes are "
+                       "kernel parameters; the whole mesh (vertices, colours, normals, triangles) lands in host memory every step"}
 
+    clocks = sampler.stop() if sampler else None          # sampled over all timed regions above (main loop, fused, e2e)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         val, tris, d = cpu_baseline(args.scene, args.cpu_n, 3, 1)

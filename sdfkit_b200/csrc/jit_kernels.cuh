@@ -39,12 +39,13 @@ struct sdfk_sample_params {
 
 // Sign blocks: a by-product of sampling that lets marching cubes find the active cells without re-reading the
 // distance field (1 bit per voxel instead of 4 bytes).  A warp walks its column (128 x of one y) in z, so every lane
-// keeps the signs of its 4 voxels over 8 consecutive z slices in ONE register and the warp stores 32 words = 128
-// contiguous bytes per 8 slices:  signs[((y*tiles_per_row + xc)*nzb + zl/8)*32 + L], bit 4*(zl%8) + k  <->  voxel
-// (xc*128 + 4L + k, y, zl) has value > iso (strict, Cell.cs:221-228; evaluated on the value actually stored, i.e.
-// after ClipToBounds).  nzb = ceil(nzl/8).  Bits of voxels beyond the row / slab are unspecified / zero; the consumer
-// (mc_classify_signs, mc_kernels.cu) masks the cells that do not exist.  z segments of a split column are 8-aligned,
-// so a word has exactly one writer.
+// keeps the signs of its 4 voxels over 8 consecutive z slices in ONE register, four such registers make a uint4, and
+// the warp stores 32 uint4 = 512 contiguous bytes per 32 slices:
+//     signs[((y*tiles_per_row + xc)*nzg + zl/32)*32 + L]   (uint4; nzg = ceil(nzl/32))
+//     word (zl/8)%4, bit 4*(zl%8) + k   <->   voxel (xc*128 + 4L + k, y, zl) has value > iso
+// (strict, Cell.cs:221-228; evaluated on the value actually stored, i.e. after ClipToBounds).  Bits of voxels beyond
+// the row / slab are unspecified / zero; the consumer (mc_classify_signs, mc_kernels.cu) masks the cells that do not
+// exist.  z segments of a split column are 32-aligned, so a uint4 has exactly one writer.
 static __device__ __forceinline__ unsigned sdfk_gt_mask(float a, float b)   // 0xFFFFFFFF if a > b (false for NaN) else 0: one FSET
 {
     unsigned m;
@@ -63,8 +64,8 @@ static __device__ __forceinline__ unsigned sdfk_sign_nibble(const float* d, floa
 static __device__ __forceinline__ void sdfk_zsegment(const sdfk_sample_params& P, unsigned seg, int& zl0, int& zl1)
 {
     const long long a = ((long long)seg * P.nzl) / P.zsplit, b = ((long long)(seg + 1) * P.nzl) / P.zsplit;
-    zl0 = seg == 0u ? 0 : min(P.nzl, (int)((a + 7) & ~7ll));
-    zl1 = seg + 1u == P.zsplit ? P.nzl : min(P.nzl, (int)((b + 7) & ~7ll));
+    zl0 = seg == 0u ? 0 : min(P.nzl, (int)((a + 31) & ~31ll));
+    zl1 = seg + 1u == P.zsplit ? P.nzl : min(P.nzl, (int)((b + 31) & ~31ll));
 }
 
 // Device layout (DESIGN.md "data layout"): x fastest.  dist[(zl*ny + y)*nx + x], rgb[((zl*ny + y)*nx + x)*3 + c],
@@ -77,7 +78,7 @@ static __device__ __forceinline__ void sdfk_zsegment(const sdfk_sample_params& P
 // neighbouring columns, so at any moment the grid is writing a few contiguous planes.  Streaming
 // (evict-first) stores: the field is write-once.
 extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
-sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __restrict__ rgb, unsigned* __restrict__ signs)
+sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __restrict__ rgb, uint4* __restrict__ signs)
 {
     __shared__ float4 stage[SDFK_SAMPLE_WARPS][96];
     const unsigned lane = threadIdx.x & 31u;
@@ -108,9 +109,11 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
         const int nvalid = min(128, P.nx - (int)(xc * 128u));
         const int nq = (nvalid * 3) >> 2;                          // float4s of colour per tile on the vector path
         size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
-        unsigned* const scol = signs + ((size_t)uy * P.tiles_per_row + xc) * (size_t)((P.nzl + 7) >> 3) * 32u + lane;   // this lane's sign words
+        uint4* const scol = signs + ((size_t)uy * P.tiles_per_row + xc) * (size_t)((P.nzl + 31) >> 5) * 32u + lane;   // this lane's sign words
 
-        for (int zb0 = zl0; zb0 < zl1; zb0 += 8) {                  // zl0 is a multiple of 8: one sign word per lane and z-block
+        for (int zg0 = zl0; zg0 < zl1; zg0 += 32) {                 // zl0 is a multiple of 32: one uint4 of signs per lane and 32 slices
+        uint4 sw = make_uint4(0u, 0u, 0u, 0u);
+        for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {   // one 32-bit sign word per lane and 8 slices
         const int zend = min(zb0 + 8, zl1);
         unsigned sacc = 0u, ssh = 0u;
         for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
@@ -156,7 +159,10 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
                 }
             }
         }
-        if (signs) scol[(size_t)(zb0 >> 3) * 32u] = sacc;
+        const int sq = (zb0 >> 3) & 3;
+        if (sq == 0) sw.x = sacc; else if (sq == 1) sw.y = sacc; else if (sq == 2) sw.z = sacc; else sw.w = sacc;
+        }
+        if (signs) __stcs(scol + (size_t)(zg0 >> 5) * 32u, sw);     // evict-first like the voxel stream (a second cache policy in the stream costs 3 %)
         }
     }
 }
@@ -165,7 +171,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
 // instead of 16; the colours marching cubes needs (two corners per created vertex) are evaluated afterwards by
 // sdfk_k_vertex_colors.  Same traversal and arithmetic as sdfk_k_sample.
 extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
-sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, unsigned* __restrict__ signs)
+sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* __restrict__ signs)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = threadIdx.x >> 5;
@@ -196,9 +202,11 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, unsigne
             setb[k] = w ? __float_as_uint(P.clip_value) : 0u;
         }
         size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xc * 128u);   // first voxel of the tile
-        unsigned* const scol = signs + ((size_t)uy * P.tiles_per_row + xc) * (size_t)((P.nzl + 7) >> 3) * 32u + lane;   // this lane's sign words
+        uint4* const scol = signs + ((size_t)uy * P.tiles_per_row + xc) * (size_t)((P.nzl + 31) >> 5) * 32u + lane;   // this lane's sign words
 
-        for (int zb0 = zl0; zb0 < zl1; zb0 += 8) {                  // zl0 is a multiple of 8: one sign word per lane and z-block
+        for (int zg0 = zl0; zg0 < zl1; zg0 += 32) {                 // zl0 is a multiple of 32: one uint4 of signs per lane and 32 slices
+        uint4 sw = make_uint4(0u, 0u, 0u, 0u);
+        for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {   // one 32-bit sign word per lane and 8 slices
         const int zend = min(zb0 + 8, zl1);
         unsigned sacc = 0u, ssh = 0u;
         for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
@@ -227,7 +235,10 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, unsigne
                 }
             }
         }
-        if (signs) scol[(size_t)(zb0 >> 3) * 32u] = sacc;
+        const int sq = (zb0 >> 3) & 3;
+        if (sq == 0) sw.x = sacc; else if (sq == 1) sw.y = sacc; else if (sq == 2) sw.z = sacc; else sw.w = sacc;
+        }
+        if (signs) __stcs(scol + (size_t)(zg0 >> 5) * 32u, sw);     // evict-first like the voxel stream (a second cache policy in the stream costs 3 %)
         }
     }
 }

@@ -584,7 +584,8 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
 // K2' mc_classify_signs: the outputs of mc_classify (active cells + 128-bit activity mask per chunk) from the SIGN
 // BLOCKS the sampling kernels write as a by-product (csrc/jit_kernels.cuh) -- 1 bit per voxel instead of the 4-byte
 // distance, so the distance field is never re-read to find the surface.  step == 1 only (voxel tiles == cell chunks).
-// Layout: signs[((y*tpr + xc)*nzb + zb)*32 + L], bit 4p + k <-> voxel (xc*128 + 4L + k, y, 8*zb + p) has value > iso.
+// Layout: uint4 signs[((y*tpr + xc)*nzg + zg)*32 + L]; word zb%4 of group zg = zb/4, bit 4p + k <-> voxel
+// (xc*128 + 4L + k, y, 8*zb + p) has value > iso.
 // A warp takes one (row j, chunk xc) column and MC_SZB z-blocks (all loads issued up front): per block two coalesced 128-byte loads
 // (rows j, j+1) give every lane the signs of its 4 x 2 x 8 voxels; the x neighbour comes from lane L+1 (lane 31: the
 // next tile), the z neighbour from the next bit plane (plane 7: the next block).
@@ -592,33 +593,44 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
 #define MC_SZB 8
 
 __global__ void __launch_bounds__(256)
-mc_classify_signs_kernel(const McGrid g, const unsigned* __restrict__ signs, unsigned tpr, unsigned nzb, unsigned* __restrict__ counts,
-                         uint4* __restrict__ masks, unsigned ncols, unsigned nwork, int zb_first, int zb_last)
+mc_classify_signs_kernel(const McGrid g, const uint4* __restrict__ signs, unsigned tpr, unsigned nzg, unsigned* __restrict__ counts,
+                         uint4* __restrict__ masks, unsigned ncols, unsigned nwork, int zg_first, int zb_last)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int off = g.k0 - g.z0;                                          // plane zl = local layer kl + off  (step == 1)
-    const size_t colwords = (size_t)nzb * 32u;
+    const size_t colwords = (size_t)nzg * 32u;                            // uint4s per (row, tile) column
     const unsigned sh = 4u * (lane & 7u);
     for (unsigned w = gw; w < nwork; w += nw) {
         const unsigned seg = w / ncols, col = w - seg * ncols;
         const unsigned j = col / (unsigned)g.cpr, xc = col - j * (unsigned)g.cpr;
-        const int zb0 = zb_first + (int)(seg * MC_SZB);
-        const unsigned* rowA = signs + ((size_t)j * tpr + xc) * colwords + (size_t)zb0 * 32u + lane;
-        const unsigned* rowB = rowA + (size_t)tpr * colwords;
+        const int zg0 = zg_first + (int)(seg * (MC_SZB / 4)), zb0 = zg0 * 4;
+        const uint4* rowA = signs + ((size_t)j * tpr + xc) * colwords + (size_t)zg0 * 32u + lane;
+        const uint4* rowB = rowA + (size_t)tpr * colwords;
         const bool edge = lane == 31u && xc + 1u < tpr;                   // lane 31's x neighbour: lane 0's word of the next tile
         // cells of this lane that exist (i = xc*128 + 4L + k < ncx), replicated over the 8 planes
         const int left = g.ncx - (int)(xc * 128u + lane * 4u);
         const unsigned cellmask = (left >= 4 ? 15u : (left <= 0 ? 0u : ((1u << left) - 1u))) * 0x11111111u;
-        // all loads of the item first (blocks zb0 .. zb0 + MC_SZB, the last one only for its first plane)
+        // all loads of the item first: two groups of 4 blocks per row as uint4, + the first block of the next group (only its
+        // first plane is needed); lane 31 also fetches lane 0's words of the next tile
         unsigned a[MC_SZB + 1], b[MC_SZB + 1], an[MC_SZB + 1], bn[MC_SZB + 1];
-#pragma unroll
-        for (int q = 0; q <= MC_SZB; q++) {
-            const bool in = zb0 + q < (int)nzb;
-            a[q] = in ? __ldg(rowA + q * 32) : 0u;
-            b[q] = in ? __ldg(rowB + q * 32) : 0u;
-            an[q] = (in && edge) ? __ldg(rowA + q * 32 + colwords - 31) : 0u;
-            bn[q] = (in && edge) ? __ldg(rowB + q * 32 + colwords - 31) : 0u;
+        {
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            const bool in0 = zg0 < (int)nzg, in1 = zg0 + 1 < (int)nzg, in2 = zg0 + 2 < (int)nzg;
+            const uint4 a0 = in0 ? __ldg(rowA) : z4, a1 = in1 ? __ldg(rowA + 32) : z4;
+            const uint4 b0 = in0 ? __ldg(rowB) : z4, b1 = in1 ? __ldg(rowB + 32) : z4;
+            a[8] = in2 ? __ldg(reinterpret_cast<const unsigned*>(rowA + 64)) : 0u;
+            b[8] = in2 ? __ldg(reinterpret_cast<const unsigned*>(rowB + 64)) : 0u;
+            const uint4* nA = rowA + colwords - 31;
+            const uint4* nB = rowB + colwords - 31;
+            const uint4 c0 = (in0 && edge) ? __ldg(nA) : z4, c1 = (in1 && edge) ? __ldg(nA + 32) : z4;
+            const uint4 d0 = (in0 && edge) ? __ldg(nB) : z4, d1 = (in1 && edge) ? __ldg(nB + 32) : z4;
+            an[8] = (in2 && edge) ? __ldg(reinterpret_cast<const unsigned*>(nA + 64)) : 0u;
+            bn[8] = (in2 && edge) ? __ldg(reinterpret_cast<const unsigned*>(nB + 64)) : 0u;
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            an[0] = c0.x; an[1] = c0.y; an[2] = c0.z; an[3] = c0.w; an[4] = c1.x; an[5] = c1.y; an[6] = c1.z; an[7] = c1.w;
+            bn[0] = d0.x; bn[1] = d0.y; bn[2] = d0.z; bn[3] = d0.w; bn[4] = d1.x; bn[5] = d1.y; bn[6] = d1.z; bn[7] = d1.w;
         }
         unsigned any[MC_SZB + 1], all[MC_SZB + 1];                        // OR / AND over rows j, j+1 and voxels c, c+1; bit 4p + k
 #pragma unroll
@@ -666,14 +678,14 @@ mc_classify_signs_kernel(const McGrid g, const unsigned* __restrict__ signs, uns
     }
 }
 
-cudaError_t mc_launch_classify_signs(const McGrid& g, const unsigned* signs, unsigned tiles_per_row, unsigned nzb, unsigned* counts,
+cudaError_t mc_launch_classify_signs(const McGrid& g, const uint4* signs, unsigned tiles_per_row, unsigned nzg, unsigned* counts,
                                      uint4* masks, cudaStream_t s)
 {
     if (g.nchunks == 0) return cudaSuccess;
     if (g.step != 1 || g.k0 < g.z0) return cudaErrorInvalidValue;
     const int off = g.k0 - g.z0;
-    const int zb_first = off >> 3, zb_last = (off + g.nk - 1) >> 3;        // z-blocks holding the lower plane of a classified layer
-    const unsigned ncols = (unsigned)g.ncy * (unsigned)g.cpr, nseg = (unsigned)(zb_last - zb_first + MC_SZB) / MC_SZB;
+    const int zg_first = off >> 5, zb_last = (off + g.nk - 1) >> 3;        // z-groups / z-blocks holding the lower plane of a classified layer
+    const unsigned ncols = (unsigned)g.ncy * (unsigned)g.cpr, nseg = (unsigned)(zb_last - zg_first * 4 + MC_SZB) / MC_SZB;
     const unsigned long long nwork = (unsigned long long)ncols * nseg;   // <= nchunks < 2^32
     if (nwork > 0xFFFFFFFFull) return cudaErrorInvalidValue;
     int dev = 0, sms = 148;
@@ -681,7 +693,7 @@ cudaError_t mc_launch_classify_signs(const McGrid& g, const unsigned* signs, uns
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     unsigned long long blocks = (nwork + 7) / 8;
     if (blocks > (unsigned long long)sms * 8u) blocks = (unsigned long long)sms * 8u;
-    mc_classify_signs_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, signs, tiles_per_row, nzb, counts, masks, ncols, (unsigned)nwork, zb_first, zb_last);
+    mc_classify_signs_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, signs, tiles_per_row, nzg, counts, masks, ncols, (unsigned)nwork, zg_first, zb_last);
     return cudaGetLastError();
 }
 
@@ -690,7 +702,7 @@ cudaError_t mc_launch_classify_signs(const McGrid& g, const unsigned* signs, uns
 // order.  Single pass: warp-shuffle scans inside a tile, decoupled look-back between tiles.
 // ---------------------------------------------------------------------------------------------------
 #define SCAN_THREADS 256
-#define SCAN_ITEMS 4
+#define SCAN_ITEMS 16
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
 struct ScanWs {

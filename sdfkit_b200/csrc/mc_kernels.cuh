@@ -75,7 +75,7 @@ struct McEmitParams {
 cudaError_t mc_init_tables();
 cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* counts, uint4* masks, cudaStream_t s);
 // same outputs from the sign planes written by the sampling kernels (step == 1): no pass over the distance field
-cudaError_t mc_launch_classify_signs(const McGrid& g, const unsigned* signs, unsigned tiles_per_row, unsigned nzb, unsigned* counts,
+cudaError_t mc_launch_classify_signs(const McGrid& g, const uint4* signs, unsigned tiles_per_row, unsigned nzg, unsigned* counts,
                                      uint4* masks, cudaStream_t s);
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
                            McTotals* totals, cudaStream_t s);
