@@ -295,18 +295,17 @@ __device__ static inline size_t mc_vox(const McGrid& g, int i, int j, int kg, in
     return ((size_t)zl * g.ny + y) * (size_t)g.nx + x;
 }
 
-// values of the 8 cube corners minus iso, as doubles, reference corner numbering (Cell.cs:206-213)
+// values of the 8 cube corners minus iso, as doubles, reference corner numbering (Cell.cs:206-213): one base address,
+// then constant strides (x: step, y: step*nx, z: step*nx*ny)
 __device__ static inline void mc_load_cell(const McGrid& g, const float* __restrict__ dist, int i, int j, int kg, double* v)
 {
     const double iso = (double)g.iso;
-    v[0] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 0, 0)) - iso;
-    v[1] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 0, 0)) - iso;
-    v[2] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 1, 0)) - iso;
-    v[3] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 1, 0)) - iso;
-    v[4] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 0, 1)) - iso;
-    v[5] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 0, 1)) - iso;
-    v[6] = (double)__ldg(dist + mc_vox(g, i, j, kg, 1, 1, 1)) - iso;
-    v[7] = (double)__ldg(dist + mc_vox(g, i, j, kg, 0, 1, 1)) - iso;
+    const size_t sx = (size_t)g.step, sy = (size_t)g.step * (size_t)g.nx, sz = (size_t)g.step * (size_t)g.nx * (size_t)g.ny;
+    const float* p = dist + mc_vox(g, i, j, kg, 0, 0, 0);
+    const float f0 = __ldg(p), f1 = __ldg(p + sx), f2 = __ldg(p + sx + sy), f3 = __ldg(p + sy);
+    const float f4 = __ldg(p + sz), f5 = __ldg(p + sz + sx), f6 = __ldg(p + sz + sx + sy), f7 = __ldg(p + sz + sy);
+    v[0] = (double)f0 - iso; v[1] = (double)f1 - iso; v[2] = (double)f2 - iso; v[3] = (double)f3 - iso;
+    v[4] = (double)f4 - iso; v[5] = (double)f5 - iso; v[6] = (double)f6 - iso; v[7] = (double)f7 - iso;
 }
 
 
@@ -902,10 +901,12 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __re
                 i = (int)(xc * 128u) + mc_nth_set_bit(sm, q);
                 const int kg = g.k0 + kl;
                 float f[8];
-                f[0] = __ldg(dist + mc_vox(g, i, j, kg, 0, 0, 0)); f[1] = __ldg(dist + mc_vox(g, i, j, kg, 1, 0, 0));
-                f[2] = __ldg(dist + mc_vox(g, i, j, kg, 1, 1, 0)); f[3] = __ldg(dist + mc_vox(g, i, j, kg, 0, 1, 0));
-                f[4] = __ldg(dist + mc_vox(g, i, j, kg, 0, 0, 1)); f[5] = __ldg(dist + mc_vox(g, i, j, kg, 1, 0, 1));
-                f[6] = __ldg(dist + mc_vox(g, i, j, kg, 1, 1, 1)); f[7] = __ldg(dist + mc_vox(g, i, j, kg, 0, 1, 1));
+                {
+                    const size_t sx = (size_t)g.step, sy = (size_t)g.step * (size_t)g.nx, sz = (size_t)g.step * (size_t)g.nx * (size_t)g.ny;
+                    const float* p = dist + mc_vox(g, i, j, kg, 0, 0, 0);
+                    f[0] = __ldg(p); f[1] = __ldg(p + sx); f[2] = __ldg(p + sx + sy); f[3] = __ldg(p + sy);
+                    f[4] = __ldg(p + sz); f[5] = __ldg(p + sz + sx); f[6] = __ldg(p + sz + sx + sy); f[7] = __ldg(p + sz + sy);
+                }
                 int idx = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) idx |= (f[k] > iso ? 1 : 0) << k;
