@@ -223,7 +223,7 @@ def run_ours(args):
     # dram__bytes_read + dram__bytes_write of one K1 launch from the committed ncu capture (same workload only)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01s2_k1_traffic.json")))
         if world == 1 and n == 1024 and args.scene == "readme":
             traffic = float(tj["traffic_bytes"])
     except Exception:
@@ -292,43 +292,42 @@ def run_ours(args):
             e_s = (time.perf_counter() - e0) / e_steps
             d2h = mesh.Vertices.nbytes * 3 + mesh.Triangles.nbytes + 24
         else:
-            pinned = {}
-
-            def to_host(name, t):
-                """device tensor -> recycled page-locked host tensor (grown on demand)"""
-                buf = pinned.get(name)
-                if buf is None or buf.numel() < t.numel():
-                    buf = pinned[name] = torch.empty(int(t.numel() * 1.25) + 16, dtype=t.dtype, pin_memory=True)
-                out = buf[:t.numel()].view(t.shape)
-                out.copy_(t, non_blocking=True)
-                return out
+            # N ranks: every rank delivers ITS share of the mesh (global indices from the count all-gather) into its own
+            # page-locked host memory over its own PCIe link (sdfk_mesh_emit_host: emit in sub-ranges, copies overlapped);
+            # the job's mesh is the concatenation of the shares in rank order
+            ejob = skd.ShardedMesher(sdf, mn, mx, n, n, n, rank, world, spr, clip=True,
+                                     balanced=(world > 1 and not args.uniform_slabs), colors=False)
 
             def e2e_step():
-                step()
-                parts = [torch.cat(ps) for ps in zip(*[skd.mesh_device_tensors(s_.mesh, dev) for s_ in job.slabs if s_.mesh is not None])]
-                cnt = skd.all_gather_int64([parts[0].shape[0], parts[3].shape[0]], device=dev)
-                outs = [skd.gather_rows(p, cnt[:, 1 if i == 3 else 0]) for i, p in enumerate(parts)]
-                if rank == 0:
-                    host = [to_host(i, o) for i, o in enumerate(outs)]
-                    torch.cuda.synchronize()
-                    return sum(h.numel() * h.element_size() for h in host)
-                return 0
-            e2e_step()
+                counts = ejob.sample_classify()
+                allc = skd.all_gather_int64(counts, device=dev)
+                offs, _ = ejob.offsets(allc)
+                parts = ejob.emit_host(offs)
+                return sum(m.Vertices.nbytes * 3 + m.Triangles.nbytes + 24 for m in parts)
+            for _ in range(2):
+                e2e_step()
             barrier()
             e0 = time.perf_counter()
             for _ in range(e_steps):
                 d2h = e2e_step()
             barrier()
             e_s = (time.perf_counter() - e0) / e_steps
+            ejob.close()
+            tb = torch.tensor([float(d2h)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tb)
+            d2h = int(tb.item())
         te = torch.tensor([e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_s = te.item()
         e2e = {"value": nvox_total / e_s, "unit": UNIT, "ms_per_step": e_s * 1e3, "h2d_bytes_per_step": 256,
                "d2h_bytes_per_step": int(d2h),
-               "note": "Sdf.ToMesh through the host API (sdfk_sdf_to_mesh_host: z-slabs pipelined, mesh parts streamed to page-locked "
-                       "host memory while the next slabs are computed); the SDF is analytic so the only host->device bytes are "
-                       "kernel parameters; the whole mesh (vertices, colours, normals, triangles) lands in host memory every step"}
+               "note": ("Sdf.ToMesh through the host API (sdfk_sdf_to_mesh_host: z-slabs pipelined, mesh parts streamed to page-locked "
+                        "host memory while the next slabs are computed)" if world == 1 else
+                        "per rank: distance-only sampling + classify, NCCL all-gather of the counts, chunked emit with every part "
+                        "streamed to the rank's own page-locked host memory (sdfk_mesh_emit_host); d2h bytes summed over ranks") +
+                       "; the SDF is analytic so the only host->device bytes are kernel parameters; the whole mesh (vertices, "
+                       "colours, normals, triangles) lands in host memory every step"}
 
     clocks = sampler.stop() if sampler else None          # sampled over all timed regions above (main loop, fused, e2e)
     cpu = None

@@ -67,15 +67,30 @@ namespace SdfKit.B200
             return voxels;
         }
 
-        /// SdfEx.ToMesh (SdfKit/Sdf.cs:59-63): the voxels stay in HBM, only the mesh comes back
+        /// SdfEx.ToMesh (SdfKit/Sdf.cs:59-63): one native call.  The grid is sampled (distances only) and meshed in z-slabs on
+        /// the device while the finished parts of the mesh stream to page-locked host memory owned by the native handle;
+        /// the managed arrays are filled from there (Buffer.MemoryCopy, one pass per array).
         public static Mesh ToMesh(Sdf sdf, Vector3 min, Vector3 max, int nx, int ny, int nz, bool clipToBounds,
                                   float isoValue, int step, IProgress<float>? progress)
         {
             var g = GpuSdf.Require(sdf);
-            Native.Check(Native.sdfk_voxels_sample(g.Context.Ptr, g.Ptr, (float*)&min, (float*)&max, nx, ny, nz,
-                clipToBounds ? 1 : 0, out var vox));
-            try { return CreateMesh(g.Context, vox, min, max, nx, ny, nz, isoValue, step, progress); }
-            finally { Native.sdfk_voxels_destroy(vox); }
+            MeshTransforms(min, max, nx, ny, nz, out var transform, out var normalTransform);
+            Native.ProgressFn? cb = progress is null ? null : (f, _) => progress.Report(f);
+            Native.Check(Native.sdfk_sdf_to_mesh_host(g.Context.Ptr, g.Ptr, (float*)&min, (float*)&max, nx, ny, nz,
+                clipToBounds ? 1 : 0, isoValue, step, (float*)&transform, (float*)&normalTransform, 0, cb, IntPtr.Zero, out var mesh));
+            GC.KeepAlive(cb);
+            try {
+                Native.Check(Native.sdfk_mesh_counts(mesh, out var nv, out var ntri));
+                Native.Check(Native.sdfk_mesh_host_ptrs(mesh, out var hv, out var hc, out var hn, out var ht));
+                var v = new Vector3[nv]; var c = new Vector3[nv]; var n = new Vector3[nv]; var t = new int[ntri * 3];
+                fixed (Vector3* pv = v) fixed (Vector3* pc = c) fixed (Vector3* pn = n) fixed (int* pt = t) {
+                    Buffer.MemoryCopy(hv, pv, nv * 12, nv * 12);
+                    Buffer.MemoryCopy(hc, pc, nv * 12, nv * 12);
+                    Buffer.MemoryCopy(hn, pn, nv * 12, nv * 12);
+                    Buffer.MemoryCopy(ht, pt, ntri * 12, ntri * 12);
+                }
+                return new Mesh(v, c, n, t);
+            } finally { Native.sdfk_mesh_destroy(mesh); }
         }
 
         /// MarchingCubes.CreateMesh (SdfKit/MarchingCubes.cs:39-92) on host-built voxels
@@ -91,18 +106,23 @@ namespace SdfKit.B200
             finally { Native.sdfk_voxels_destroy(vox); }
         }
 
-        static Mesh CreateMesh(GpuContext ctx, IntPtr vox, Vector3 min, Vector3 max, int nx, int ny, int nz,
-                               float iso, int step, IProgress<float>? progress)
+        /// the very matrices of MarchingCubes.cs:85-90 and Mesh.cs:49-55, computed with System.Numerics itself
+        static void MeshTransforms(Vector3 min, Vector3 max, int nx, int ny, int nz, out Matrix4x4 transform, out Matrix4x4 normalTransform)
         {
-            // the very matrices of MarchingCubes.cs:85-90 and Mesh.cs:49-55, computed with System.Numerics itself
             var size = max - min;
-            var transform =
+            transform =
                 Matrix4x4.CreateTranslation(-(nx - 1) / 2f, -(ny - 1) / 2f, -(nz - 1) / 2f) *
                 Matrix4x4.CreateScale(size.X / (nx - 1), size.Y / (ny - 1), size.Z / (nz - 1)) *
                 Matrix4x4.CreateTranslation((min + max) * 0.5f);
             var nt = transform; nt.M41 = 0; nt.M42 = 0; nt.M43 = 0; nt.M44 = 1;
             Matrix4x4.Invert(nt, out var inv);
-            var normalTransform = Matrix4x4.Transpose(inv);
+            normalTransform = Matrix4x4.Transpose(inv);
+        }
+
+        static Mesh CreateMesh(GpuContext ctx, IntPtr vox, Vector3 min, Vector3 max, int nx, int ny, int nz,
+                               float iso, int step, IProgress<float>? progress)
+        {
+            MeshTransforms(min, max, nx, ny, nz, out var transform, out var normalTransform);
             Native.ProgressFn? cb = progress is null ? null : (f, _) => progress.Report(f);
             Native.Check(Native.sdfk_mesh_create(ctx.Ptr, vox, iso, step, (float*)&transform, (float*)&normalTransform,
                 cb, IntPtr.Zero, out var mesh));

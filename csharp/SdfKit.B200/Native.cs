@@ -36,6 +36,12 @@ namespace SdfKit.B200
         [DllImport(Lib)] public static extern int sdfk_mesh_counts(IntPtr mesh, out long nverts, out long ntris);
         [DllImport(Lib)] public static extern int sdfk_mesh_export(IntPtr mesh, float* vertices, float* colors, float* normals,
             int* triangles, float* aabb);
+        [DllImport(Lib)] public static extern int sdfk_sdf_to_mesh_host(IntPtr ctx, IntPtr sdf, float* min, float* max,
+            int nx, int ny, int nz, int clip, float iso, int step, float* transform, float* normalTransform, int nslabs,
+            ProgressFn? progress, IntPtr user, out IntPtr mesh);
+        [DllImport(Lib)] public static extern int sdfk_mesh_host_ptrs(IntPtr mesh, out float* vertices, out float* colors,
+            out float* normals, out int* triangles);
+        [DllImport(Lib)] public static extern int sdfk_ctx_set_option(IntPtr ctx, int option, int value);
         [DllImport(Lib)] public static extern int sdfk_mesh_destroy(IntPtr mesh);
 
         [DllImport(Lib)] public static extern int sdfk_render(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos, float* invViewProj,

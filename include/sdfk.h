@@ -125,6 +125,12 @@ int sdfk_mesh_classify(sdfk_ctx* ctx, sdfk_voxels* vox, float iso, int step, int
                        sdfk_mesh** out, int64_t* nverts, int64_t* ntris);
 int sdfk_mesh_emit(sdfk_mesh* mesh, int64_t vertex_base, int64_t triangle_base, const float transform[16],
                    const float normal_transform[16]);
+/* sdfk_mesh_emit with the result delivered to HOST memory: the owned cell layers are emitted in `nchunks` sub-ranges
+ * (0 = automatic) and every finished part streams to page-locked host memory (owned by the mesh handle, see
+ * sdfk_mesh_host_ptrs) on a copy stream while the next sub-range is computed -- in a multi-GPU job every rank moves its
+ * share of the mesh over its own PCIe link.  Returns when the arrays are complete. */
+int sdfk_mesh_emit_host(sdfk_mesh* mesh, int64_t vertex_base, int64_t triangle_base, const float transform[16],
+                        const float normal_transform[16], int nchunks);
 int sdfk_mesh_counts(sdfk_mesh* mesh, int64_t* nverts, int64_t* ntris);
 /* SdfEx.ToMesh (Sdf.cs:59-63) in one call, with the mesh delivered to HOST memory.  The grid is cut into z-slabs
  * (nslabs; 0 = automatic: ~64 cell layers each, at most 16); each slab is sampled (distance-only voxels + sign blocks), classified,

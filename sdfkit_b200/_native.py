@@ -48,6 +48,7 @@ SIGNATURES = {
     "sdfk_mesh_create": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _fp, _fp, PROGRESS_FN, _vp, C.POINTER(_vp)]),
     "sdfk_mesh_classify": (C.c_int, [_vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _i64p, _i64p]),
     "sdfk_mesh_emit": (C.c_int, [_vp, C.c_int64, C.c_int64, _fp, _fp]),
+    "sdfk_mesh_emit_host": (C.c_int, [_vp, C.c_int64, C.c_int64, _fp, _fp, C.c_int]),
     "sdfk_mesh_counts": (C.c_int, [_vp, _i64p, _i64p]),
     "sdfk_sdf_to_mesh_host": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, C.c_int,
                                         PROGRESS_FN, _vp, C.POINTER(_vp)]),

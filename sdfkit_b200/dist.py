@@ -157,6 +157,15 @@ class SlabMesher:
         N.check(N.lib().sdfk_mesh_emit(self.mesh.handle, int(vertex_base), int(triangle_base), N.fptr(self.M), N.fptr(self.Nn)))
         return self.mesh
 
+    def emit_host(self, vertex_base, triangle_base, chunks=0):
+        """K4b in sub-ranges, each finished part streaming to page-locked host memory (sdfk_mesh_emit_host): this rank's share
+        of the mesh, with global indices, as a host Mesh (zero-copy view of the handle's buffers)."""
+        N.check(N.lib().sdfk_mesh_emit_host(self.mesh.handle, int(vertex_base), int(triangle_base), N.fptr(self.M), N.fptr(self.Nn),
+                                            int(chunks)))
+        host = self.mesh.host_view()
+        self.mesh = None                   # the views own the handle now
+        return host
+
     def voxel_count(self):
         """Voxels this rank owns for throughput accounting (halo slices are not counted)."""
         nx, ny, nz = self.dims
@@ -244,6 +253,10 @@ class ShardedMesher:
         for s, (vb, tb) in zip(self.slabs, offs):
             if s.mesh is not None:
                 s.emit(vb, tb)
+
+    def emit_host(self, offs, chunks=0):
+        """Like emit, but every slab's share of the mesh lands in this rank's page-locked host memory; returns the host Meshes."""
+        return [s.emit_host(vb, tb, chunks) for s, (vb, tb) in zip(self.slabs, offs) if s.mesh is not None]
 
     def voxel_count(self):
         return sum(s.voxel_count() for s in self.slabs)

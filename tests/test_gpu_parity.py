@@ -498,3 +498,30 @@ def test_pipelined_to_mesh_buffers_are_recycled_safely(sk):
     c = s1.ToMesh(mn, mx, 64, 64, 64)                                        # reuses a's buffers
     assert np.array_equal(c.Vertices, va) and np.array_equal(c.Triangles, ta)
     assert len(b.Vertices) == 4872
+
+
+@pytest.mark.parametrize("nslabs,chunks,colors", [(1, 0, True), (1, 5, False), (3, 4, False), (4, 16, True)])
+def test_chunked_emit_to_host_equals_single_gpu(sk, oracle, nslabs, chunks, colors):
+    """sdfk_mesh_emit_host (every rank's share of the mesh emitted in sub-ranges and streamed to its own page-locked host
+    memory, global indices from the count all-gather): the concatenated shares are the single-GPU mesh, bit for bit."""
+    from sdfkit_b200 import dist, scenes
+    expr, mn, mx = scenes.readme_scene()
+    sdf = expr.ToSdf()
+    n = 96
+    whole = sdf.ToVoxels(mn, mx, n, n, n).ToMesh()
+    jobs = [dist.ShardedMesher(sdf, mn, mx, n, n, n, r, nslabs, 1, colors=colors) for r in range(nslabs)]
+    counts = np.stack([j.sample_classify() for j in jobs])
+    parts = []
+    for j in jobs:
+        offs, tot = j.offsets(counts)
+        parts += j.emit_host(offs, chunks)
+    assert int(tot[0]) == len(whole.Vertices)
+    merged = dist.merge_meshes(parts)
+    assert np.array_equal(merged.Triangles, whole.Triangles)
+    assert_bits_equal(merged.Vertices, whole.Vertices, "emit_host vertices")
+    assert_bits_equal(merged.Normals, whole.Normals, "emit_host normals")
+    assert_bits_equal(merged.Colors, whole.Colors, "emit_host colours")
+    assert_bits_equal(merged.Min, whole.Min, "emit_host aabb min")
+    assert_bits_equal(merged.Max, whole.Max, "emit_host aabb max")
+    for j in jobs:
+        j.close()
