@@ -79,6 +79,13 @@ int sdfk_sdf_compile(sdfk_ctx* ctx, const char* body, size_t len, sdfk_sdf** out
 int sdfk_sdf_destroy(sdfk_sdf* sdf);
 /* NVRTC-compile only (needs no GPU): validates a body and reports the cubin size. */
 int sdfk_sdf_check(const char* body, size_t len, size_t* cubin_bytes);
+/* The packed (two points per instruction, add/mul/fma.rn.f32x2) form of an SDF body may divide by a constant with a
+ * 3-instruction correctly rounded sequence instead of the generic IEEE division.  Before emitting it for a constant the
+ * host side asks the device to compare it with div.rn.f32 for ALL 2^32 dividends (a few ms, cached by the caller);
+ * mismatches != 0 means: keep the generic division for this constant.  sdfk_selftest_sqrt does the same for the packed
+ * square root (all 2^32 arguments against sqrt.rn.f32). */
+int sdfk_constdiv_verify(sdfk_ctx* ctx, float divisor, int64_t* mismatches);
+int sdfk_selftest_sqrt(sdfk_ctx* ctx, int64_t* mismatches);
 /* the Sdf delegate itself (Sdf.cs:8): rgbd[i] = sdf(xyz[i]); host pointers, n*3 floats in, n*4 out */
 int sdfk_sdf_eval(sdfk_sdf* sdf, const float* xyz, float* rgbd, int64_t n);
 

@@ -34,6 +34,8 @@ SIGNATURES = {
     "sdfk_sdf_destroy": (C.c_int, [_vp]),
     "sdfk_sdf_check": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sdfk_sdf_eval": (C.c_int, [_vp, _fp, _fp, C.c_int64]),
+    "sdfk_constdiv_verify": (C.c_int, [_vp, C.c_float, _i64p]),
+    "sdfk_selftest_sqrt": (C.c_int, [_vp, _i64p]),
     "sdfk_voxels_sample": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "sdfk_voxels_sample_slab": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(_vp)]),
@@ -195,6 +197,25 @@ class Context:
         n = C.c_int64()
         check(lib().sdfk_ctx_launch_count(self.handle, C.byref(n)))
         return n.value
+
+    def constdiv_ok(self, divisor):
+        """May the packed SDF body divide by this float32 constant with the 3-instruction sequence (sk2_divc)?  Decided by an
+        exhaustive comparison with IEEE division on this context's GPU (all 2^32 dividends), once per constant."""
+        d = np.float32(divisor)
+        if not np.isfinite(d) or d == 0 or not (2.0 ** -30 <= abs(float(d)) <= 2.0 ** 30):
+            return False
+        cache = self.__dict__.setdefault("_constdiv", {})
+        key = d.tobytes()
+        if key not in cache:
+            bad = C.c_int64()
+            check(lib().sdfk_constdiv_verify(self.handle, C.c_float(float(d)), C.byref(bad)))
+            cache[key] = bad.value == 0
+        return cache[key]
+
+    def selftest_sqrt(self):
+        bad = C.c_int64()
+        check(lib().sdfk_selftest_sqrt(self.handle, C.byref(bad)))
+        return bad.value
 
     def set_option(self, option, value):
         check(lib().sdfk_ctx_set_option(self.handle, int(option), int(value)))

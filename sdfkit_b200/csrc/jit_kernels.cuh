@@ -122,13 +122,15 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
             const bool zwall = P.clip && (iz == 0 || iz == P.nz - 1);
             float d[4];
             float c[12];
+            sk_float4 r4[4];
+            sdf_eval2(sk_make3(px[0], py, pz), sk_make3(px[1], py, pz), r4[0], r4[1]);     // two voxels per call: packed f32x2
+            sdf_eval2(sk_make3(px[2], py, pz), sk_make3(px[3], py, pz), r4[2], r4[3]);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const sk_float4 r = sdf_eval(sk_make3(px[k], py, pz));
-                d[k] = (zwall || xywall[k]) ? P.clip_value : r.w;
-                c[3 * k + 0] = r.x;
-                c[3 * k + 1] = r.y;
-                c[3 * k + 2] = r.z;
+                d[k] = (zwall || xywall[k]) ? P.clip_value : r4[k].w;
+                c[3 * k + 0] = r4[k].x;
+                c[3 * k + 1] = r4[k].y;
+                c[3 * k + 2] = r4[k].z;
             }
 #ifndef SDFK_X_NOSIGNS
             sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
@@ -216,9 +218,12 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
                 d[0] = d[1] = d[2] = d[3] = P.clip_value;
             } else {
                 const float pz = P.m2 + (float)iz * P.dz;
+                sk_float4 r4[4];
+                sdf_eval2(sk_make3(px[0], py, pz), sk_make3(px[1], py, pz), r4[0], r4[1]);     // two voxels per call: packed f32x2
+                sdf_eval2(sk_make3(px[2], py, pz), sk_make3(px[3], py, pz), r4[2], r4[3]);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    d[k] = __uint_as_float((__float_as_uint(sdf_eval(sk_make3(px[k], py, pz)).w) & keep[k]) | setb[k]);
+                    d[k] = __uint_as_float((__float_as_uint(r4[k].w) & keep[k]) | setb[k]);
             }
 #ifndef SDFK_X_NOSIGNS
             sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
@@ -257,14 +262,14 @@ struct sdfk_color_params {
     int k0;                         // global cell layer of local layer 0 of the cell ids
 };
 
-static __device__ __forceinline__ void sdfk_corner(const sdfk_color_params& P, const float* __restrict__ dist, int i, int j, int kg,
-                                                   int dxc, int dyc, int dzc, double& w, float& r, float& g, float& b)
+// weight and sample position of corner (dxc, dyc, dzc) of cell (i, j, kg)
+static __device__ __forceinline__ sk_float3 sdfk_corner(const sdfk_color_params& P, const float* __restrict__ dist, int i, int j, int kg,
+                                                        int dxc, int dyc, int dzc, double& w)
 {
     const int x = (i + dxc) * P.step, y = (j + dyc) * P.step, z = (kg + dzc) * P.step;
     const float v = dist[((size_t)(z - P.z0) * P.ny + y) * (size_t)P.nx + x];
     w = 1.0 / (0.0000001 + fabs((double)v - (double)P.iso));
-    const sk_float4 c = sdf_eval(sk_make3(P.m0 + (float)x * P.dx, P.m1 + (float)y * P.dy, P.m2 + (float)z * P.dz));
-    r = c.x; g = c.y; b = c.z;
+    return sk_make3(P.m0 + (float)x * P.dx, P.m1 + (float)y * P.dy, P.m2 + (float)z * P.dz);
 }
 
 extern "C" __global__ void __launch_bounds__(128)
@@ -284,28 +289,34 @@ sdfk_k_vertex_colors(const sdfk_color_params P, const uint2* __restrict__ recipe
         if (rc.y < 12u) {
             const int a = end1[rc.y], c = end2[rc.y];
             double w1, w2;
-            float r1, g1, b1, r2, g2, b2;
-            sdfk_corner(P, dist, i, j, kg, a & 1, (a >> 1) & 1, a >> 2, w1, r1, g1, b1);
-            sdfk_corner(P, dist, i, j, kg, c & 1, (c >> 1) & 1, c >> 2, w2, r2, g2, b2);
+            const sk_float3 p1 = sdfk_corner(P, dist, i, j, kg, a & 1, (a >> 1) & 1, a >> 2, w1);
+            const sk_float3 p2 = sdfk_corner(P, dist, i, j, kg, c & 1, (c >> 1) & 1, c >> 2, w2);
+            sk_float4 c1, c2;
+            sdf_eval2(p1, p2, c1, c2);                              // both end corners in one packed evaluation
             double ff = 0.0;
             ff += w1;
             ff += w2;
             const float f1 = (float)w1, f2 = (float)w2;
-            cr = (float)((double)(r1 * f1 + r2 * f2) / ff);
-            cg = (float)((double)(g1 * f1 + g2 * f2) / ff);
-            cb = (float)((double)(b1 * f1 + b2 * f2) / ff);
+            cr = (float)((double)(c1.x * f1 + c2.x * f2) / ff);
+            cg = (float)((double)(c1.y * f1 + c2.y * f2) / ff);
+            cb = (float)((double)(c1.z * f1 + c2.z * f2) / ff);
         } else {   // centre vertex: corners 0..7 in the reference's numbering
             double ff = 0.0;
             float fr = 0.f, fg = 0.f, fb = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                double w;
-                float r, g, b;
-                sdfk_corner(P, dist, i, j, kg, (0x66 >> q) & 1, (0xCC >> q) & 1, (0xF0 >> q) & 1, w, r, g, b);
-                ff += w;
-                const float wq = (float)w;
-                if (q == 0) { fr = r * wq; fg = g * wq; fb = b * wq; }
-                else { fr = fr + r * wq; fg = fg + g * wq; fb = fb + b * wq; }
+            for (int q = 0; q < 8; q += 2) {
+                double wa, wb;
+                const sk_float3 pa = sdfk_corner(P, dist, i, j, kg, (0x66 >> q) & 1, (0xCC >> q) & 1, (0xF0 >> q) & 1, wa);
+                const sk_float3 pb = sdfk_corner(P, dist, i, j, kg, (0x66 >> (q + 1)) & 1, (0xCC >> (q + 1)) & 1, (0xF0 >> (q + 1)) & 1, wb);
+                sk_float4 ca, cb4;
+                sdf_eval2(pa, pb, ca, cb4);
+                ff += wa;
+                const float fa = (float)wa;
+                if (q == 0) { fr = ca.x * fa; fg = ca.y * fa; fb = ca.z * fa; }
+                else { fr = fr + ca.x * fa; fg = fg + ca.y * fa; fb = fb + ca.z * fa; }
+                ff += wb;
+                const float fbw = (float)wb;
+                fr = fr + cb4.x * fbw; fg = fg + cb4.y * fbw; fb = fb + cb4.z * fbw;
             }
             cr = (float)((double)fr / ff);
             cg = (float)((double)fg / ff);
@@ -321,9 +332,13 @@ sdfk_k_vertex_colors(const sdfk_color_params P, const uint2* __restrict__ recipe
 extern "C" __global__ void __launch_bounds__(256)
 sdfk_k_eval(const float* __restrict__ xyz, float* __restrict__ rgbd, long long n)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const sk_float4 r = sdf_eval(sk_make3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
-        reinterpret_cast<float4*>(rgbd)[i] = make_float4(r.x, r.y, r.z, r.w);
+    const long long npair = (n + 1) >> 1;                             // two points per thread: packed f32x2 evaluation
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npair; q += (long long)gridDim.x * blockDim.x) {
+        const long long i = 2 * q, i1 = (i + 1 < n) ? i + 1 : i;
+        sk_float4 r0, r1;
+        sdf_eval2(sk_make3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), sk_make3(xyz[3 * i1], xyz[3 * i1 + 1], xyz[3 * i1 + 2]), r0, r1);
+        reinterpret_cast<float4*>(rgbd)[i] = make_float4(r0.x, r0.y, r0.z, r0.w);
+        if (i1 != i) reinterpret_cast<float4*>(rgbd)[i1] = make_float4(r1.x, r1.y, r1.z, r1.w);
     }
 }
 
@@ -351,48 +366,64 @@ static __device__ __forceinline__ sk_float3 sdfk_ray_dir(const sdfk_render_param
     return sk_make3(dx / len, dy / len, dz / len);
 }
 
-// One thread per pixel; the reference's ~12 full-image temporaries per iteration live in registers.
+// Shading of one pixel from its march result (RayMarcher.cs:146-160): gradient taps already evaluated.
+static __device__ __forceinline__ void sdfk_shade(const sdfk_render_params& P, float sx, float sy, float sz, float depth, float cr, float cg, float cb,
+                                                  float px, float py, float pz, float mx, float my, float mz, float* __restrict__ out)
+{
+    float nx = px - mx, ny = py - my, nz = pz - mz;
+    const float nl = sk_sqrt(nx * nx + ny * ny + nz * nz);     // NormalizeInplace (VectorData.cs:490-510)
+    if (nl > 0.0f) { const float r = 1.0f / nl; nx = nx * r; ny = ny * r; nz = nz * r; }
+    float lx = 5.0f - sx, ly = 5.0f - sy, lz = 10.0f - sz;     // light (5,5,10) (RayMarcher.cs:149-150)
+    const float ll = sk_sqrt(lx * lx + ly * ly + lz * lz);
+    if (ll > 0.0f) { const float r = 1.0f / ll; lx = lx * r; ly = ly * r; lz = lz * r; }
+    float dv = nx * lx + ny * ly + nz * lz;                    // Dot (VectorData.cs:464-475)
+    dv = (dv != dv) ? dv : ((dv > 0.0f) ? dv : 0.0f);          // MaxInplace(0): MathF.Max, NaN propagates
+    const float mask = depth > P.farp ? 1.0f : 0.0f;           // bgMask (RayMarcher.cs:156)
+    const float notmask = mask == 0.0f ? 1.0f : 0.0f;
+    // fg = (dv*colour + 0.1) * notmask + mask*bg ; frag(=0) += fg  (RayMarcher.cs:154-160)
+    out[0] = 0.0f + ((dv * cr + 0.1f) * notmask + mask * 0.5f);
+    out[1] = 0.0f + ((dv * cg + 0.1f) * notmask + mask * 0.75f);
+    out[2] = 0.0f + ((dv * cb + 0.1f) * notmask + mask * 1.0f);
+}
+
+// One thread per PAIR of neighbouring pixels (every SDF evaluation is a packed two-point sdf_eval2); the reference's ~12
+// full-image temporaries per iteration live in registers.
 extern "C" __global__ void __launch_bounds__(128)
 sdfk_k_render(const sdfk_render_params P, float* __restrict__ rgb)
 {
     const long long npix = (long long)(P.row_end - P.row_begin) * P.w;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
-        const int j = P.row_begin + (int)(pix / P.w);
-        const int i = (int)(pix % P.w);
-        const sk_float3 rd = sdfk_ray_dir(P, i, j);
-        float depth = P.nearp - 0.1f;                              // RayMarcher.cs:136
-        float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    const long long npair = (npix + 1) >> 1;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npair; q += (long long)gridDim.x * blockDim.x) {
+        const long long pa = 2 * q, pb = (pa + 1 < npix) ? pa + 1 : pa;
+        const sk_float3 ra = sdfk_ray_dir(P, (int)(pa % P.w), P.row_begin + (int)(pa / P.w));
+        const sk_float3 rb = sdfk_ray_dir(P, (int)(pb % P.w), P.row_begin + (int)(pb / P.w));
+        float da = P.nearp - 0.1f, db = P.nearp - 0.1f;            // RayMarcher.cs:136
+        float ca[3] = {0.0f, 0.0f, 0.0f}, cb[3] = {0.0f, 0.0f, 0.0f};
         for (int it = 0; it < P.iters; it++) {                     // fixed count, no early out (RayMarcher.cs:138-145)
-            const sk_float4 s = sdf_eval(sk_make3(rd.x * depth + P.cam[0], rd.y * depth + P.cam[1], rd.z * depth + P.cam[2]));
-            depth = depth + s.w;
-            if (it == P.iters - 1) { cr = cr + s.x; cg = cg + s.y; cb = cb + s.z; }
+            sk_float4 s0, s1;
+            sdf_eval2(sk_make3(ra.x * da + P.cam[0], ra.y * da + P.cam[1], ra.z * da + P.cam[2]),
+                      sk_make3(rb.x * db + P.cam[0], rb.y * db + P.cam[1], rb.z * db + P.cam[2]), s0, s1);
+            da = da + s0.w;
+            db = db + s1.w;
+            if (it == P.iters - 1) {
+                ca[0] = ca[0] + s0.x; ca[1] = ca[1] + s0.y; ca[2] = ca[2] + s0.z;
+                cb[0] = cb[0] + s1.x; cb[1] = cb[1] + s1.y; cb[2] = cb[2] + s1.z;
+            }
         }
-        const float sx = P.cam[0] + rd.x * depth, sy = P.cam[1] + rd.y * depth, sz = P.cam[2] + rd.z * depth;
-        // DistanceGradient: taps +x,+y,+z,-x,-y,-z at GradOffset = 1e-5 (RayMarcher.cs:29,164-204)
+        const float ax = P.cam[0] + ra.x * da, ay = P.cam[1] + ra.y * da, az = P.cam[2] + ra.z * da;
+        const float bx = P.cam[0] + rb.x * db, by = P.cam[1] + rb.y * db, bz = P.cam[2] + rb.z * db;
+        // DistanceGradient: taps +x,+y,+z,-x,-y,-z at GradOffset = 1e-5 (RayMarcher.cs:29,164-204), pixel a and pixel b per call
         const float go = 1e-5f;
-        const float px = sdf_eval(sk_make3(sx + go * 1.0f, sy + go * 0.0f, sz + go * 0.0f)).w;
-        const float py = sdf_eval(sk_make3(sx + go * 0.0f, sy + go * 1.0f, sz + go * 0.0f)).w;
-        const float pz = sdf_eval(sk_make3(sx + go * 0.0f, sy + go * 0.0f, sz + go * 1.0f)).w;
-        const float mx = sdf_eval(sk_make3(sx + -go * 1.0f, sy + -go * 0.0f, sz + -go * 0.0f)).w;
-        const float my = sdf_eval(sk_make3(sx + -go * 0.0f, sy + -go * 1.0f, sz + -go * 0.0f)).w;
-        const float mz = sdf_eval(sk_make3(sx + -go * 0.0f, sy + -go * 0.0f, sz + -go * 1.0f)).w;
-        float nx = px - mx, ny = py - my, nz = pz - mz;
-        const float nl = sk_sqrt(nx * nx + ny * ny + nz * nz);     // NormalizeInplace (VectorData.cs:490-510)
-        if (nl > 0.0f) { const float r = 1.0f / nl; nx = nx * r; ny = ny * r; nz = nz * r; }
-        float lx = 5.0f - sx, ly = 5.0f - sy, lz = 10.0f - sz;     // light (5,5,10) (RayMarcher.cs:149-150)
-        const float ll = sk_sqrt(lx * lx + ly * ly + lz * lz);
-        if (ll > 0.0f) { const float r = 1.0f / ll; lx = lx * r; ly = ly * r; lz = lz * r; }
-        float dv = nx * lx + ny * ly + nz * lz;                    // Dot (VectorData.cs:464-475)
-        dv = (dv != dv) ? dv : ((dv > 0.0f) ? dv : 0.0f);          // MaxInplace(0): MathF.Max, NaN propagates
-        const float mask = depth > P.farp ? 1.0f : 0.0f;           // bgMask (RayMarcher.cs:156)
-        const float notmask = mask == 0.0f ? 1.0f : 0.0f;
-        // fg = (dv*colour + 0.1) * notmask + mask*bg ; frag(=0) += fg  (RayMarcher.cs:154-160)
-        const float r0 = 0.0f + ((dv * cr + 0.1f) * notmask + mask * 0.5f);
-        const float g0 = 0.0f + ((dv * cg + 0.1f) * notmask + mask * 0.75f);
-        const float b0 = 0.0f + ((dv * cb + 0.1f) * notmask + mask * 1.0f);
-        rgb[pix * 3 + 0] = r0;
-        rgb[pix * 3 + 1] = g0;
-        rgb[pix * 3 + 2] = b0;
+        sk_float4 t0, t1;
+        float ga[6], gb[6];
+        sdf_eval2(sk_make3(ax + go * 1.0f, ay + go * 0.0f, az + go * 0.0f), sk_make3(bx + go * 1.0f, by + go * 0.0f, bz + go * 0.0f), t0, t1); ga[0] = t0.w; gb[0] = t1.w;
+        sdf_eval2(sk_make3(ax + go * 0.0f, ay + go * 1.0f, az + go * 0.0f), sk_make3(bx + go * 0.0f, by + go * 1.0f, bz + go * 0.0f), t0, t1); ga[1] = t0.w; gb[1] = t1.w;
+        sdf_eval2(sk_make3(ax + go * 0.0f, ay + go * 0.0f, az + go * 1.0f), sk_make3(bx + go * 0.0f, by + go * 0.0f, bz + go * 1.0f), t0, t1); ga[2] = t0.w; gb[2] = t1.w;
+        sdf_eval2(sk_make3(ax + -go * 1.0f, ay + -go * 0.0f, az + -go * 0.0f), sk_make3(bx + -go * 1.0f, by + -go * 0.0f, bz + -go * 0.0f), t0, t1); ga[3] = t0.w; gb[3] = t1.w;
+        sdf_eval2(sk_make3(ax + -go * 0.0f, ay + -go * 1.0f, az + -go * 0.0f), sk_make3(bx + -go * 0.0f, by + -go * 1.0f, bz + -go * 0.0f), t0, t1); ga[4] = t0.w; gb[4] = t1.w;
+        sdf_eval2(sk_make3(ax + -go * 0.0f, ay + -go * 0.0f, az + -go * 1.0f), sk_make3(bx + -go * 0.0f, by + -go * 0.0f, bz + -go * 1.0f), t0, t1); ga[5] = t0.w; gb[5] = t1.w;
+        sdfk_shade(P, ax, ay, az, da, ca[0], ca[1], ca[2], ga[0], ga[1], ga[2], ga[3], ga[4], ga[5], rgb + pa * 3);
+        if (pb != pa) sdfk_shade(P, bx, by, bz, db, cb[0], cb[1], cb[2], gb[0], gb[1], gb[2], gb[3], gb[4], gb[5], rgb + pb * 3);
     }
 }
 
@@ -400,15 +431,20 @@ extern "C" __global__ void __launch_bounds__(128)
 sdfk_k_render_depth(const sdfk_render_params P, float* __restrict__ depth_out)
 {
     const long long npix = (long long)(P.row_end - P.row_begin) * P.w;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
-        const int j = P.row_begin + (int)(pix / P.w);
-        const int i = (int)(pix % P.w);
-        const sk_float3 rd = sdfk_ray_dir(P, i, j);
-        float depth = P.nearp - 0.1f;
+    const long long npair = (npix + 1) >> 1;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npair; q += (long long)gridDim.x * blockDim.x) {
+        const long long pa = 2 * q, pb = (pa + 1 < npix) ? pa + 1 : pa;
+        const sk_float3 ra = sdfk_ray_dir(P, (int)(pa % P.w), P.row_begin + (int)(pa / P.w));
+        const sk_float3 rb = sdfk_ray_dir(P, (int)(pb % P.w), P.row_begin + (int)(pb / P.w));
+        float da = P.nearp - 0.1f, db = P.nearp - 0.1f;
         for (int it = 0; it < P.iters; it++) {
-            const sk_float4 s = sdf_eval(sk_make3(rd.x * depth + P.cam[0], rd.y * depth + P.cam[1], rd.z * depth + P.cam[2]));
-            depth = depth + s.w;
+            sk_float4 s0, s1;
+            sdf_eval2(sk_make3(ra.x * da + P.cam[0], ra.y * da + P.cam[1], ra.z * da + P.cam[2]),
+                      sk_make3(rb.x * db + P.cam[0], rb.y * db + P.cam[1], rb.z * db + P.cam[2]), s0, s1);
+            da = da + s0.w;
+            db = db + s1.w;
         }
-        depth_out[pix] = depth;
+        depth_out[pa] = da;
+        if (pb != pa) depth_out[pb] = db;
     }
 }

@@ -35,8 +35,15 @@ class GpuSdf:
     def __init__(self, expr, ctx=None):
         self.ctx = ctx or N.Context.default()
         self.expr = expr
-        self.lowered = lower(expr)
-        body = self.lowered.body.encode()
+        # SDFK_PACKED=1: also emit the packed two-points-per-instruction body (add/mul/fma.rn.f32x2, verified fast division by
+        # constants).  Bit-identical results, 40 % fewer instructions in the ray-march loop -- and measured SLOWER on B200
+        # (README ToImage 0.189 -> 0.236 ms, CSG-50 sampling 10.8 -> 16.5 ms: register pairs, per-half traffic), so it is off
+        # by default; DESIGN.md section 2b.
+        import os
+        from .exprs import PACKED_MARKER
+        packed = os.environ.get("SDFK_PACKED", "0") == "1"
+        self.lowered = lower(expr, fast_div=self.ctx.constdiv_ok if packed else None)
+        body = (self.lowered.body + ((PACKED_MARKER + "\n" + self.lowered.body2) if packed else "")).encode()
         h = C.c_void_p()
         N.check(N.lib().sdfk_sdf_compile(self.ctx.handle, body, len(body), C.byref(h)))
         self.handle = h

@@ -525,3 +525,55 @@ def test_chunked_emit_to_host_equals_single_gpu(sk, oracle, nslabs, chunks, colo
     assert_bits_equal(merged.Max, whole.Max, "emit_host aabb max")
     for j in jobs:
         j.close()
+
+
+# ---------------------------------------------------------------------------------------------- packed (f32x2) evaluator
+
+def test_packed_sqrt_is_exhaustively_exact(sk):
+    """sk2_sqrt (csrc/sdfk_prelude.h) against sqrt.rn.f32 for ALL 2^32 arguments (and scrambled partners in the other half)."""
+    from sdfkit_b200 import _native as N
+    assert N.Context.default().selftest_sqrt() == 0
+
+
+@pytest.mark.parametrize("divisor", [1.125, 6.0, 3.0, 0.1, 7.0, 2.5, 1e-3, 1023.0, 0.33333334, 1.9999999, 1.0000001, -5.0])
+def test_constant_division_is_exhaustively_exact(sk, divisor):
+    """sk2_divc for this constant against div.rn.f32 for ALL 2^32 dividends; the lowering only uses it after this check."""
+    import ctypes as C
+    from sdfkit_b200 import _native as N
+    ctx = N.Context.default()
+    bad = C.c_int64(-1)
+    N.check(N.lib().sdfk_constdiv_verify(ctx.handle, C.c_float(divisor), C.byref(bad)))
+    assert bad.value == 0, "%d of 2^32 dividends differ for divisor %r" % (bad.value, divisor)
+    assert ctx.constdiv_ok(divisor) is True
+    assert ctx.constdiv_ok(0.0) is False and ctx.constdiv_ok(float("inf")) is False and ctx.constdiv_ok(1e-20) is False
+
+
+def test_packed_body_uses_verified_fast_division(sk, monkeypatch):
+    from sdfkit_b200 import scenes
+    monkeypatch.setenv("SDFK_PACKED", "1")
+    sdf = scenes.readme_scene()[0].ToSdf()
+    assert "sk2_divc(" in sdf.lowered.body2 and len(sdf.lowered.fast_div) == 2      # / 1.125 and / 6
+    assert "sk2_sqrt(" in sdf.lowered.body2 and "sk2_add_s(" in sdf.lowered.body2
+    assert "sk2_" not in sdf.lowered.body                                            # the scalar body (what the oracle compiles) is untouched
+
+
+@pytest.mark.parametrize("name,dims", [("sphere", (33, 20, 17)), ("readme", (64, 64, 64)), ("perf", (50, 37, 29)), ("csg50", (96, 96, 48))])
+def test_packed_evaluator_is_bit_identical(sk, oracle, monkeypatch, name, dims):
+    """SDFK_PACKED=1 (two points per instruction on the f32x2 pipe; off by default because it measured slower): voxels, mesh,
+    delegate and image are still the oracle's, bit for bit."""
+    from sdfkit_b200 import numerics, scenes
+    monkeypatch.setenv("SDFK_PACKED", "1")
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    assert sdf.lowered.body2 and "sk2_" in sdf.lowered.body2
+    vox = sdf.ToVoxels(mn, mx, nx, ny, nz)
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, threads=4)
+    assert_bits_equal(vox.Values, ov, name + " packed distances")
+    assert_bits_equal(vox.Colors, oc, name + " packed colours")
+    assert_mesh_equal(sdf.ToMesh(mn, mx, nx, ny, nz), oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx)), name + " packed ToMesh")
+    pts = np.random.default_rng(5).uniform(-4, 4, (4099, 3)).astype(np.float32)
+    assert_bits_equal(sdf(pts), oracle.eval_sdf(sdf.lowered, pts), name + " packed delegate")
+    img = sdf.ToImage(97, 41, *scenes.CAMERA)
+    ref = oracle.render(sdf.lowered, 97, 41, view=numerics.create_look_at(*scenes.CAMERA), bands=2)
+    assert_bits_equal(img.Array, ref, name + " packed image")

@@ -17,7 +17,10 @@ kernel = sys.argv[2] if len(sys.argv) > 2 else "sdfk_k_sample"
 expr = {"readme": scenes.readme_scene, "csg50": scenes.csg50, "sphere": scenes.sphere, "perf": scenes.perf_scene}[name]()[0]
 csrc = os.path.join(ROOT, "sdfkit_b200", "csrc")
 src = open(os.path.join(csrc, "sdfk_prelude.h")).read()
-src += "\nSK_FN sk_float4 sdf_eval(sk_float3 p)\n{\n" + expr.Lower().body + "\n}\n"
+from sdfkit_b200.exprs import lower  # noqa: E402
+low = lower(expr, fast_div=(lambda c: True) if "--fastdiv" in sys.argv else None)
+src += "\nSK_FN sk_float4 sdf_eval(sk_float3 p)\n{\n" + low.body + "\n}\n"
+src += "SK_FN void sdf_eval2(sk_float3 p0, sk_float3 p1, sk_float4& r0, sk_float4& r1)\n{\n" + low.body2 + "\n}\n"
 src += open(os.path.join(csrc, "jit_kernels.cuh")).read()
 cu = "/tmp/sdfk_jit_%s.cu" % name
 open(cu, "w").write(src)
