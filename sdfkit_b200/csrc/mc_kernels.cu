@@ -1210,57 +1210,126 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
 
 #define MC_FOR_EDGES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11)
 
-// latency-bound (dependent lookups): more resident warps beat fewer spills -- measured 1.15 ms at 92 registers / 5 CTAs,
-// 0.94 ms at 48 registers / 10 CTAs per SM (1024^3 README scene)
-__global__ void __launch_bounds__(MC_EMIT_THREADS, 10)
-mc_emit_kernel(const McEmitParams p)
+// K4b runs as two kernels.
+//   mc_emit_tris_kernel   one thread per record: the vertex id of every slot the cell references, its triangles, and one
+//                         TASK (record, slot) per vertex the cell creates, stored at the vertex' own index.
+//   mc_emit_verts_kernel  one thread per created VERTEX.  Creating a vertex is the expensive part (FP64 interpolation, the
+//                         ordered gather of up to four cells' gradients) and its code depends on the edge the vertex sits on;
+//                         inside the per-record kernel the three interior kinds (edges 5, 6, 10) each ran with a third of
+//                         the lanes (12 of 32 lanes active on average, 5.6e8 warp instructions).  Here a block first sorts
+//                         its 1024 tasks by kind in shared memory and then works through one kind at a time with full warps.
+#define MC_VERT_THREADS 256
+#define MC_VERT_PER_BLOCK 1024
+
+__global__ void __launch_bounds__(MC_EMIT_THREADS, 12)
+mc_emit_tris_kernel(const McEmitParams p)
 {
     __shared__ int s_vid[MC_EMIT_THREADS][13];
     const McGrid& g = p.g;
     const unsigned r = p.rec_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
-    if (r < p.rec_end) {
-        McRecord rec = p.recs[r];
-        const int i = (int)(rec.cell % (unsigned)g.ncx);
-        const unsigned t2 = rec.cell / (unsigned)g.ncx;
-        const int j = (int)(t2 % (unsigned)g.ncy);
-        const int kl = (int)(t2 / (unsigned)g.ncy);
-        const int kg = g.k0 + kl;
-        {   // records carry chunk-local offsets
-            const uint4 cb = __ldg(p.base + (t2 * (unsigned)g.cpr + ((unsigned)i >> 7)));
-            rec.vbase += cb.y;
-            rec.tbase += cb.z;
-        }
-        const McRowMeta* meta = d_meta + MC_LEAF_ROW(rec.info);
-        const signed char* row = d_lut + meta->off;
-        const int nent = 3 * (int)MC_LEAF_NT(rec.info);
-        const unsigned owned = mc_owned_mask(i, j, kg);
-        const unsigned refd = nent ? meta->refmask : 0u;                // nent == 0: "impossible case 13", emits nothing
-        int* vid = s_vid[threadIdx.x];
-
-        double v[8];
-        mc_load_cell(g, p.dist, i, j, kg, v);
-
-        // ---- vertex id of every slot this cell references
+    if (r >= p.rec_end) return;
+    McRecord rec = p.recs[r];
+    const int i = (int)(rec.cell % (unsigned)g.ncx);
+    const unsigned t2 = rec.cell / (unsigned)g.ncx;
+    const int j = (int)(t2 % (unsigned)g.ncy);
+    const int kl = (int)(t2 / (unsigned)g.ncy);
+    const int kg = g.k0 + kl;
+    {   // records carry chunk-local offsets
+        const uint4 cb = __ldg(p.base + (t2 * (unsigned)g.cpr + ((unsigned)i >> 7)));
+        rec.vbase += cb.y;
+        rec.tbase += cb.z;
+    }
+    const McRowMeta* meta = d_meta + MC_LEAF_ROW(rec.info);
+    const signed char* row = d_lut + meta->off;
+    const int nent = 3 * (int)MC_LEAF_NT(rec.info);
+    const unsigned owned = mc_owned_mask(i, j, kg);
+    const unsigned refd = nent ? meta->refmask : 0u;                // nent == 0: "impossible case 13", emits nothing
+    int* vid = s_vid[threadIdx.x];
+    // ---- vertex id of every slot this cell references
 #define VID(E) if ((refd >> E) & 1u) vid[E] = mc_vertex_id<E>(p, rec, meta, owned, i, j, kl, kg);
-        MC_FOR_EDGES(VID)
+    MC_FOR_EDGES(VID)
 #undef VID
-        if ((refd >> 12) & 1u) vid[12] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[12] & owned));
-        // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
-        {
-            int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
-            const int shift = (int)(p.vglobal0 - (long long)p.vlocal0);
-            for (int k = 0; k < nent; k++) out[k] = vid[row[k]] + shift;
+    if ((refd >> 12) & 1u) vid[12] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[12] & owned));
+    // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
+    {
+        int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
+        const int shift = (int)(p.vglobal0 - (long long)p.vlocal0);
+        for (int k = 0; k < nent; k++) out[k] = vid[row[k]] + shift;
+    }
+    // ---- one task per vertex this cell creates, at the vertex' slot (= id - vlocal0)
+    unsigned mine = refd & owned;
+    while (mine) {
+        const int e = __ffs((int)mine) - 1;
+        mine &= mine - 1u;
+        p.tasks[(long long)vid[e] - (long long)p.vlocal0] = make_uint2(r, (unsigned)e);
+    }
+}
+
+// creates the vertex of task (record r, slot E) at vertex slot `slot`
+template <int E>
+__device__ static inline void mc_run_vertex_task(const McEmitParams& p, unsigned r, long long slot, unsigned* lo, unsigned* hi)
+{
+    const McGrid& g = p.g;
+    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(p.recs + r));      // cell, info, vbase, tbase
+    const unsigned long long aux = __ldg(&p.recs[r].aux);
+    const int i = (int)(ra.x % (unsigned)g.ncx);
+    const unsigned t2 = ra.x / (unsigned)g.ncx;
+    const int j = (int)(t2 % (unsigned)g.ncy);
+    const int kg = g.k0 + (int)(t2 / (unsigned)g.ncy);
+    double v[8];
+    mc_load_cell(g, p.dist, i, j, kg, v);
+    if (E == 12) mc_create_center_vertex(p, v, d_meta[MC_LEAF_ROW(ra.y)].occ[12], i, j, kg, slot, lo, hi, ra.x);
+    else mc_create_edge_vertex<(E == 12 ? 0 : E)>(p, v, (int)MC_AUX_OCC(aux, (E == 12 ? 0 : E)), i, j, kg, slot, lo, hi, ra.x);
+}
+
+__global__ void __launch_bounds__(MC_VERT_THREADS)
+mc_emit_verts_kernel(const McEmitParams p)
+{
+    __shared__ uint2 s_item[MC_VERT_PER_BLOCK];      // (record, slot E | local vertex index << 8), grouped by kind
+    __shared__ unsigned s_cnt[4], s_base[4];
+    const unsigned tid = threadIdx.x;
+    const unsigned first = p.vert_begin + blockIdx.x * MC_VERT_PER_BLOCK;
+    if (tid < 4) s_cnt[tid] = 0u;
+    __syncthreads();
+    // kind: 0 = edge 5, 1 = edge 6, 2 = edge 10 (what an interior cell creates), 3 = everything else (grid boundary, centre)
+    uint2 task[MC_VERT_PER_BLOCK / MC_VERT_THREADS];
+    unsigned kind[MC_VERT_PER_BLOCK / MC_VERT_THREADS], pos[MC_VERT_PER_BLOCK / MC_VERT_THREADS];
+#pragma unroll
+    for (int q = 0; q < MC_VERT_PER_BLOCK / MC_VERT_THREADS; q++) {
+        const unsigned loc = (unsigned)q * MC_VERT_THREADS + tid, vtx = first + loc;
+        kind[q] = 4u;
+        if (vtx < p.vert_end) {
+            task[q] = __ldg(p.tasks + vtx);
+            const unsigned e = task[q].y;
+            kind[q] = e == 5u ? 0u : (e == 6u ? 1u : (e == 10u ? 2u : 3u));
+            task[q].y = e | (loc << 8);
+            pos[q] = atomicAdd(&s_cnt[kind[q]], 1u);
         }
-        // ---- vertices this cell creates; slot = id - vlocal0
-        const unsigned mine = refd & owned;
-#define VERT(E) if ((mine >> E) & 1u) mc_create_edge_vertex<E>(p, v, (int)MC_AUX_OCC(rec.aux, E), i, j, kg, (long long)vid[E] - (long long)p.vlocal0, lo, hi, rec.cell);
-        VERT(5) VERT(6) VERT(10)
-        if (mine & 0x0B9Fu) {     // grid-boundary cells also create edges 0-4, 7-9, 11
-            VERT(0) VERT(1) VERT(2) VERT(3) VERT(4) VERT(7) VERT(8) VERT(9) VERT(11)
+    }
+    __syncthreads();
+    if (tid == 0) { s_base[0] = 0u; s_base[1] = s_cnt[0]; s_base[2] = s_cnt[0] + s_cnt[1]; s_base[3] = s_cnt[0] + s_cnt[1] + s_cnt[2]; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < MC_VERT_PER_BLOCK / MC_VERT_THREADS; q++)
+        if (kind[q] < 4u) s_item[s_base[kind[q]] + pos[q]] = task[q];
+    __syncthreads();
+    unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+#define MC_KIND(K, E)                                                                                          \
+    for (unsigned idx = tid; idx < s_cnt[K]; idx += MC_VERT_THREADS) {                                         \
+        const uint2 it = s_item[s_base[K] + idx];                                                              \
+        mc_run_vertex_task<E>(p, it.x, (long long)(first + (it.y >> 8)), lo, hi);                              \
+    }
+    MC_KIND(0, 5) MC_KIND(1, 6) MC_KIND(2, 10)
+#undef MC_KIND
+    for (unsigned idx = tid; idx < s_cnt[3]; idx += MC_VERT_THREADS) {
+        const uint2 it = s_item[s_base[3] + idx];
+        const long long slot = (long long)(first + (it.y >> 8));
+        switch (it.y & 0xFFu) {
+#define MC_CASE(E) case E: mc_run_vertex_task<E>(p, it.x, slot, lo, hi); break;
+        MC_CASE(0) MC_CASE(1) MC_CASE(2) MC_CASE(3) MC_CASE(4) MC_CASE(7) MC_CASE(8) MC_CASE(9) MC_CASE(11) MC_CASE(12)
+#undef MC_CASE
+        default: break;
         }
-#undef VERT
-        if ((mine >> 12) & 1u) mc_create_center_vertex(p, v, meta->occ[12], i, j, kg, (long long)vid[12] - (long long)p.vlocal0, lo, hi, rec.cell);
     }
     // AABB: warp min/max, then one atomic per warp and component
 #pragma unroll
@@ -1277,7 +1346,11 @@ cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
 {
     const unsigned n = p.rec_end - p.rec_begin;
     if (n == 0) return cudaSuccess;
-    mc_emit_kernel<<<(n + MC_EMIT_THREADS - 1u) / MC_EMIT_THREADS, MC_EMIT_THREADS, 0, s>>>(p);
+    mc_emit_tris_kernel<<<(n + MC_EMIT_THREADS - 1u) / MC_EMIT_THREADS, MC_EMIT_THREADS, 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    const unsigned nv = p.vert_end - p.vert_begin;
+    if (e != cudaSuccess || nv == 0) return e;
+    mc_emit_verts_kernel<<<(nv + MC_VERT_PER_BLOCK - 1u) / MC_VERT_PER_BLOCK, MC_VERT_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
