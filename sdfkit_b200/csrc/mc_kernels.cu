@@ -1282,7 +1282,10 @@ __device__ static inline void mc_run_vertex_task(const McEmitParams& p, unsigned
     else mc_create_edge_vertex<(E == 12 ? 0 : E)>(p, v, (int)MC_AUX_OCC(aux, (E == 12 ? 0 : E)), i, j, kg, slot, lo, hi, ra.x);
 }
 
-__global__ void __launch_bounds__(MC_VERT_THREADS)
+#ifndef MC_VERT_MINB
+#define MC_VERT_MINB 4    // measured at 1024^3: 3 (80 regs) 0.683 ms, 4 (64 regs) 0.655 ms, 6 (40 regs) 0.731 ms
+#endif
+__global__ void __launch_bounds__(MC_VERT_THREADS, MC_VERT_MINB)
 mc_emit_verts_kernel(const McEmitParams p)
 {
     __shared__ uint2 s_item[MC_VERT_PER_BLOCK];      // (record, slot E | local vertex index << 8), grouped by kind
