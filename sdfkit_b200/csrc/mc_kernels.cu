@@ -846,7 +846,10 @@ __device__ static inline unsigned long long mc_record_aux(unsigned leaf, int i, 
                                                  (__popc(mt->before[10] & own) << 8) | (__popc(mt->before[12] & own) << 12));
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef MC_COMPACT_MINB
+#define MC_COMPACT_MINB 4
+#endif
+__global__ void __launch_bounds__(256, MC_COMPACT_MINB)
 mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
                   const uint4* __restrict__ base, McRecord* __restrict__ recs, const uint4* __restrict__ masks)
 {

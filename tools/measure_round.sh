@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --import-source on --clock-control none -k regex:sdfk_k_sample$ --launch-skip 3 -c 1 -o $out/${tag}_k1_sample -f python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-fused > /dev/null 2>&1
 REPS=1 ncu --set full --import-source on --clock-control none -k regex:sample_dist --launch-skip 5 -c 1 -o $out/${tag}_k1d_sample_dist -f python tools/time_sample.py 1024 readme > /dev/null 2>&1
 REPS=1 ncu --set full --import-source on --clock-control none -k regex:classify_signs --launch-skip 1 -c 1 -o $out/${tag}_k2s_classify_signs -f python tools/time_sample.py 1024 readme > /dev/null 2>&1
-REPS=1 ncu --set full --import-source on --clock-control none -k regex:mc_emit --launch-skip 1 -c 1 -o $out/${tag}_k4b_emit -f python tools/time_sample.py 1024 readme > /dev/null 2>&1
+REPS=1 ncu --set full --import-source on --clock-control none -k regex:mc_emit_verts --launch-skip 1 -c 1 -o $out/${tag}_k4b_emit_verts -f python tools/time_sample.py 1024 readme > /dev/null 2>&1
 python tools/run_configs.py > $out/${tag}_configs.txt 2> $out/${tag}_configs.err
 python tools/time_tomesh.py 1024 readme > $out/${tag}_tomesh.txt 2>&1
 ls $out | grep ${tag}_ | wc -l
