@@ -295,8 +295,10 @@ def run_ours(args):
             # N ranks: every rank delivers ITS share of the mesh (global indices from the count all-gather) into its own
             # page-locked host memory over its own PCIe link (sdfk_mesh_emit_host: emit in sub-ranges, copies overlapped);
             # the job's mesh is the concatenation of the shares in rank order
+            # (slabs balanced for this path: an active cell also costs its ~60 bytes over PCIe, dist.ACTIVE_CELL_COST_E2E)
             ejob = skd.ShardedMesher(sdf, mn, mx, n, n, n, rank, world, spr, clip=True,
-                                     balanced=(world > 1 and not args.uniform_slabs), colors=False)
+                                     balanced=(world > 1 and not args.uniform_slabs), colors=False,
+                                     active_cell_cost=skd.ACTIVE_CELL_COST_E2E)
 
             def e2e_step():
                 counts = ejob.sample_classify()
@@ -304,7 +306,7 @@ def run_ours(args):
                 offs, _ = ejob.offsets(allc)
                 parts = ejob.emit_host(offs)
                 return sum(m.Vertices.nbytes * 3 + m.Triangles.nbytes + 24 for m in parts)
-            for _ in range(2):
+            for _ in range(3):
                 e2e_step()
             barrier()
             e0 = time.perf_counter()

@@ -140,7 +140,7 @@ int sdfk_mesh_emit_host(sdfk_mesh* mesh, int64_t vertex_base, int64_t triangle_b
                         const float normal_transform[16], int nchunks);
 int sdfk_mesh_counts(sdfk_mesh* mesh, int64_t* nverts, int64_t* ntris);
 /* SdfEx.ToMesh (Sdf.cs:59-63) in one call, with the mesh delivered to HOST memory.  The grid is cut into z-slabs
- * (nslabs; 0 = automatic: ~64 cell layers each, at most 16); each slab is sampled (distance-only voxels + sign blocks), classified,
+ * (nslabs; 0 = automatic: ~128 cell layers each, at most 16; a slab with a lot of surface is emitted in sub-ranges); each slab is sampled (distance-only voxels + sign blocks), classified,
  * compacted and emitted at its global vertex / triangle offsets, and its part of the mesh streams to page-locked host
  * memory on a copy stream while the following slabs are computed.  The result is identical, bit for bit and in order,
  * to sdfk_voxels_sample + sdfk_mesh_create + sdfk_mesh_export.  The arrays live in page-locked memory owned by the mesh

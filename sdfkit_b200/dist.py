@@ -58,9 +58,12 @@ def weighted_partition(weights, parts):
 # cost of one active cell (compact + emit) in units of one voxel (sample + classify), measured on B200 at 1024^3:
 # (0.17 + 0.90 ms) / 3.9e6 cells  vs  (2.63 + 0.77 + 0.17 ms) / 1.07e9 voxels
 ACTIVE_CELL_COST = 82.0
+# the same when every rank also delivers its share of the mesh to host memory (e2e): an active cell then costs its compact +
+# emit time plus ~60 bytes (1 vertex, 2 triangles) over PCIe at ~54 GB/s = 1.3 ns, a voxel of the distance-only path 1.1 ps
+ACTIVE_CELL_COST_E2E = 1200.0
 
 
-def plan_layers(sdf, vmin, vmax, nx, ny, nz, parts, step=1, clip=True, coarse=128):
+def plan_layers(sdf, vmin, vmax, nx, ny, nz, parts, step=1, clip=True, coarse=128, active_cell_cost=ACTIVE_CELL_COST):
     """Cut the cell layers into `parts` contiguous slabs of near-equal COST instead of equal thickness.  A z-slab job is
     as slow as its busiest rank, and the surface of a scene is rarely spread evenly in z (the README scene fills 18 % of
     the layers).  The per-layer work is estimated from a coarse meshing pass of the same SDF on this GPU (every rank
@@ -89,7 +92,7 @@ def plan_layers(sdf, vmin, vmax, nx, ny, nz, parts, step=1, clip=True, coarse=12
     scale = (nz / c)
     fine_layer = np.minimum((np.arange(ncz) * step * c) // nz, c - 1)
     active = 0.5 * tri_per_layer[fine_layer] * scale * step
-    weights = float(nx) * ny * step + ACTIVE_CELL_COST * active
+    weights = float(nx) * ny * step + float(active_cell_cost) * active
     return weighted_partition(weights, parts)
 
 
@@ -222,10 +225,10 @@ class ShardedMesher:
     of one extra halo per slab.  Global ids stay layer-major: offsets are exclusive sums over the slabs in order g."""
 
     def __init__(self, sdf, vmin, vmax, nx, ny, nz, rank, world, slabs_per_rank=1, clip=True, iso=0.0, step=1, balanced=False,
-                 colors=True):
+                 colors=True, active_cell_cost=ACTIVE_CELL_COST):
         self.rank, self.world, self.spr = int(rank), int(world), int(slabs_per_rank)
         if balanced:
-            layers = plan_layers(sdf, vmin, vmax, nx, ny, nz, self.world * self.spr, step, clip)
+            layers = plan_layers(sdf, vmin, vmax, nx, ny, nz, self.world * self.spr, step, clip, active_cell_cost=active_cell_cost)
         else:
             layers = partition(cells_along(nz, step), self.world * self.spr)
         self.layers = layers
