@@ -577,3 +577,43 @@ def test_packed_evaluator_is_bit_identical(sk, oracle, monkeypatch, name, dims):
     img = sdf.ToImage(97, 41, *scenes.CAMERA)
     ref = oracle.render(sdf.lowered, 97, 41, view=numerics.create_look_at(*scenes.CAMERA), bands=2)
     assert_bits_equal(img.Array, ref, name + " packed image")
+
+
+def test_nan_and_inf_distances_classify_like_the_reference(sk, oracle):
+    """An SDF that produces NaN (sqrt of a negative number) and +-inf (division by zero): `value > iso` is false for NaN in the
+    reference (Cell.cs:221-228), so NaN corners count as inside.  Sign blocks (K2'), the distance classifier (K2) and the oracle
+    must agree on the active cells and the index buffer (positions next to a NaN are NaN themselves: compared as bits)."""
+    from sdfkit_b200 import _native as N
+    expr = sk.SdfExprs.Solid(lambda p: sk.MathF.Sqrt(p.X + 0.31) + (p.Y * p.Y + p.Z * p.Z - 0.36) / (p.Z * p.Z))
+    sdf = expr.ToSdf()
+    mn, mx, n = (-1, -1, -1), (1, 1, 1), 33                      # 33: z = 0 is sampled exactly -> a division by zero plane
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), n, n, n, threads=4)
+    assert np.isnan(ov).any() and np.isinf(ov).any()
+    om = oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx))
+    ctx = sdf.ctx
+    try:
+        for opt in (1, 0):
+            ctx.set_option(N.OPT_SIGN_PLANES, opt)
+            vox = sdf.ToVoxels(mn, mx, n, n, n)
+            assert_bits_equal(vox.Values, ov, "NaN/inf distances")
+            m = vox.ToMesh()
+            assert np.array_equal(m.Triangles.reshape(-1, 3), om.triangles), "sign planes %d" % opt
+            assert_bits_equal(m.Vertices, om.vertices, "vertices (sign planes %d)" % opt)
+            assert_bits_equal(m.Normals, om.normals, "normals (sign planes %d)" % opt)
+            f = sdf.ToMesh(mn, mx, n, n, n, slabs=3)
+            assert np.array_equal(f.Triangles, m.Triangles)
+            assert_bits_equal(f.Vertices, m.Vertices, "pipelined vertices (sign planes %d)" % opt)
+    finally:
+        ctx.set_option(N.OPT_SIGN_PLANES, 1)
+
+
+def test_delegate_edge_cases(sk, oracle):
+    from sdfkit_b200 import scenes
+    sdf = scenes.perf_scene()[0].ToSdf()
+    assert sdf(np.zeros((0, 3), dtype=np.float32)).shape == (0, 4)                      # empty batch
+    one = np.float32([[0.25, -0.5, 1.0]])
+    assert_bits_equal(sdf(one), oracle.eval_sdf(sdf.lowered, one), "single point")       # odd count: the pair kernel's tail
+    odd = np.random.default_rng(1).uniform(-3, 3, (2049, 3)).astype(np.float32)          # one more than the reference's batch size
+    assert_bits_equal(sdf(odd), oracle.eval_sdf(sdf.lowered, odd), "2049 points")
+    with pytest.raises(ValueError):
+        sdf(odd, np.zeros((5, 4), dtype=np.float32))
