@@ -211,6 +211,9 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
         for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {   // one 32-bit sign word per lane and 8 slices
         const int zend = min(zb0 + 8, zl1);
         unsigned sacc = 0u, ssh = 0u;
+#ifdef SDFK_X_UNROLL
+#pragma unroll SDFK_X_UNROLL
+#endif
         for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
             const int iz = zl + P.z_begin;
             float d[4];

@@ -1111,11 +1111,22 @@ __device__ static inline void mc_gather_from(const McEmitParams& p, int ci, int 
     if (ci < 0 || cj < 0 || ck < 0 || ci >= g.ncx || cj >= g.ncy || ck >= g.ncz) return;
     const int ckl = ck - g.k0;
     if (ckl < 0 || ckl >= g.nk) { atomicExch(p.error_flag, 3); return; }
-    const int sr = mc_find_record(p, ci, cj, ckl);
-    if (sr < 0) { atomicExch(p.error_flag, 4); return; }
-    const int times = (int)MC_AUX_OCC(__ldg(&p.recs[sr].aux), ES);
     double sv[8];
     mc_load_cell(g, p.dist, ci, cj, ck, sv);
+    // how often the sharing cell's tiling row references the edge: for an unambiguous cube index (nearly always) straight from
+    // the tables (no record lookup: the corners are needed anyway), else from the cell's record
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) idx |= (sv[k] > 0.0 ? 1 : 0) << k;
+    const unsigned quick = __ldg(&d_quick[idx]);
+    int times;
+    if (!(quick & MC_QUICK_AMBIG)) {
+        times = (int)d_meta[MC_LEAF_ROW(quick & 0x7FFFu)].occ[ES];
+    } else {
+        const int sr = mc_find_record(p, ci, cj, ckl);
+        if (sr < 0) { atomicExch(p.error_flag, 4); return; }
+        times = (int)MC_AUX_OCC(__ldg(&p.recs[sr].aux), ES);
+    }
     mc_add_edge_gradients<ES>(sv, times, nsum);
 }
 

@@ -1,3 +1,1 @@
-compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x -k "pipelined and (dims1 or dims4 or dims6) or chunked_emit or white_noise_all" > gpurun_out/s2_memcheck.log 2>&1
-grep -m3 -A12 "Invalid\|Error\|error:" gpurun_out/s2_memcheck.log | head -60
-grep -c "Invalid" gpurun_out/s2_memcheck.log
+for d in "" "-DSDFK_X_UNROLL=2" "-DSDFK_X_UNROLL=4" "-DSDFK_X_UNROLL=8"; do echo "== $d"; SDFK_JIT_DEFINES="$d" python tools/time_sample.py 1024 readme | tail -1; done
