@@ -542,7 +542,7 @@ mc_classify_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __r
                     w |= __shfl_xor_sync(FULL, w, 4);
                     if ((lane & 7u) == 0u && r < nrows) mw[(size_t)r * cpr * 4] = w;
                 }
-                if ((int)lane < nrows) cnt_out[(size_t)lane * cpr] = mine;
+                if ((int)lane < nrows) cnt_out[(size_t)lane * cpr] = MC_CNT_FIRST(mine);
             }
             cnt_out += (size_t)ncy * cpr;
             mask_out += (size_t)ncy * cpr;
@@ -660,7 +660,7 @@ mc_classify_signs_kernel(const McGrid g, const uint4* __restrict__ signs, unsign
             t = (t & 0x33333333u) + ((t >> 2) & 0x33333333u);                           // nibble p = active cells of layer p in this lane
             const unsigned ce = __reduce_add_sync(FULL, t & 0x0F0F0F0Fu);               // byte q = layer 2q
             const unsigned co = __reduce_add_sync(FULL, (t >> 4) & 0x0F0F0F0Fu);        // byte q = layer 2q + 1
-            if (cnt_lane) *cnt_out = (((lane & 1u) ? co : ce) >> (8u * ((lane >> 1) & 3u))) & 0xFFu;
+            if (cnt_lane) { const unsigned nc = (((lane & 1u) ? co : ce) >> (8u * ((lane >> 1) & 3u))) & 0xFFu; *cnt_out = MC_CNT_FIRST(nc); }
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 const int kl = kl_base + p;
@@ -850,8 +850,9 @@ __device__ static inline unsigned long long mc_record_aux(unsigned leaf, int i, 
 #define MC_COMPACT_MINB 4
 #endif
 __global__ void __launch_bounds__(256, MC_COMPACT_MINB)
-mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __restrict__ counts,
-                  const uint4* __restrict__ base, McRecord* __restrict__ recs, const uint4* __restrict__ masks)
+mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned* __restrict__ counts,
+                  const uint4* __restrict__ base, McRecord* __restrict__ recs, const uint4* __restrict__ masks,
+                  unsigned* __restrict__ acounts)
 {
     __shared__ unsigned s_quick[256];
     s_quick[threadIdx.x & 255u] = d_quick[threadIdx.x & 255u];
@@ -874,8 +875,8 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __re
         if (total == 0u) continue;
         const unsigned pre = incl - nact;                         // items of the chunks before mine
         uint4 mymask = make_uint4(0, 0, 0, 0);
-        unsigned myslot = 0;
-        if (nact) { mymask = masks[myc]; myslot = base[myc].x; }
+        unsigned myslot = 0, myrank = 0;                          // first record slot / rank among the ACTIVE chunks
+        if (nact) { mymask = masks[myc]; const uint2 b2 = *reinterpret_cast<const uint2*>(base + myc); myslot = b2.x; myrank = b2.y; }
         unsigned carry = 0;                                       // packed counts of the leading chunk's items in earlier batches
         for (unsigned b = 0; b < total; b += 32u) {
             const unsigned t = b + lane;
@@ -889,7 +890,7 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __re
                 if (probe < 32u && v <= t) lo += (unsigned)step;
             }
             const unsigned src = valid ? min(lo, 31u) : 0u;
-            const unsigned spre = __shfl_sync(FULL, pre, src), snact = __shfl_sync(FULL, nact, src), sslot = __shfl_sync(FULL, myslot, src);
+            const unsigned spre = __shfl_sync(FULL, pre, src), snact = __shfl_sync(FULL, nact, src), sslot = __shfl_sync(FULL, myslot, src), srank = __shfl_sync(FULL, myrank, src);
             uint4 sm;
             sm.x = __shfl_sync(FULL, mymask.x, src); sm.y = __shfl_sync(FULL, mymask.y, src);
             sm.z = __shfl_sync(FULL, mymask.z, src); sm.w = __shfl_sync(FULL, mymask.w, src);
@@ -936,7 +937,7 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __re
                 r.aux = mc_record_aux(leaf, i, j, kg);
                 r.pad = 0;
                 recs[sslot + q] = r;
-                if (q + 1u == snact) counts[c0 + src] = within + cnt;   // last cell of the chunk: its full packed counts
+                if (q + 1u == snact) acounts[srank] = within + cnt;     // last cell of the chunk: its full packed counts, by active-chunk rank
             }
             // carry for a chunk that continues into the next batch: totals of its items seen so far
             const unsigned last_within = __shfl_sync(FULL, within + cnt, 31);
@@ -945,8 +946,8 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, unsigned* __re
     }
 }
 
-cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
-                              McRecord* recs, const uint4* masks, cudaStream_t s)
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+                              McRecord* recs, const uint4* masks, unsigned* acounts, cudaStream_t s)
 {
     if (g.nchunks == 0) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -955,7 +956,7 @@ cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* coun
     unsigned groups = (g.nchunks + 31u) / 32u;
     unsigned blocks = (groups + 7u) / 8u;
     if (blocks > (unsigned)sms * 8u) blocks = (unsigned)sms * 8u;
-    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks);
+    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks, acounts);
     return cudaGetLastError();
 }
 
@@ -972,7 +973,6 @@ __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j,
     const McGrid& g = p.g;
     const unsigned chunk = ((unsigned)kl * (unsigned)g.ncy + (unsigned)j) * (unsigned)g.cpr + ((unsigned)i >> 7);
     const uint4 b = __ldg(p.base + chunk);
-    if (chunk_vbase) *chunk_vbase = b.y;
     const uint4 m = __ldg(p.masks + chunk);       // garbage for inactive chunks: only used when the count says active
     if (MC_CNT_ACT(b.w) == 0u) return -1;
     const unsigned q = (unsigned)i & 127u, w = q >> 5, bit = q & 31u;      // natural order: bit q of the 128-bit mask
@@ -982,6 +982,7 @@ __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j,
     if (w > 0) rank += __popc(m.x);
     if (w > 1) rank += __popc(m.y);
     if (w > 2) rank += __popc(m.z);
+    if (chunk_vbase) *chunk_vbase = __ldg(&p.abase[b.y].y);      // vertex prefix of the chunk, by its rank among the active chunks
     return (int)(b.x + rank);
 }
 
@@ -1249,7 +1250,8 @@ mc_emit_tris_kernel(const McEmitParams p)
     const int kl = (int)(t2 / (unsigned)g.ncy);
     const int kg = g.k0 + kl;
     {   // records carry chunk-local offsets
-        const uint4 cb = __ldg(p.base + (t2 * (unsigned)g.cpr + ((unsigned)i >> 7)));
+        const unsigned arank = __ldg(&p.base[t2 * (unsigned)g.cpr + ((unsigned)i >> 7)].y);
+        const uint4 cb = __ldg(p.abase + arank);
         rec.vbase += cb.y;
         rec.tbase += cb.z;
     }
@@ -1379,6 +1381,22 @@ __global__ void mc_readback_kernel(const unsigned* __restrict__ src, unsigned* _
 {
     for (unsigned k = threadIdx.x; k < nwords; k += blockDim.x) dst[k] = src[k];
     __threadfence_system();
+}
+
+// (records, vertices, triangles) before chunk `idx` in visiting order, to mapped host memory: the record prefix is per
+// chunk (base), the vertex / triangle prefixes per ACTIVE chunk (abase, indexed by the number of active chunks before idx)
+__global__ void mc_boundary_kernel(const uint4* __restrict__ base, const uint4* __restrict__ abase, size_t idx, uint4* __restrict__ dst)
+{
+    const uint4 b = base[idx];
+    const uint4 a = abase[b.y];
+    *dst = make_uint4(b.x, a.y, a.z, 0u);
+    __threadfence_system();
+}
+
+cudaError_t mc_launch_boundary(const uint4* base, const uint4* abase, size_t idx, void* dst_host_mapped, cudaStream_t s)
+{
+    mc_boundary_kernel<<<1, 1, 0, s>>>(base, abase, idx, (uint4*)dst_host_mapped);
+    return cudaGetLastError();
 }
 
 cudaError_t mc_launch_readback(const void* src_dev, void* dst_host_mapped, unsigned nwords, cudaStream_t s)

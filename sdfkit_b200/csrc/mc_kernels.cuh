@@ -39,6 +39,9 @@ struct __align__(32) McRecord {
 #define MC_CNT_V(c) (((c) >> 8) & 0x7FFu)
 #define MC_CNT_T(c) (((c) >> 19) & 0x7FFu)
 #define MC_CNT_PACK(a, v, t) ((unsigned)(a) | ((unsigned)(v) << 8) | ((unsigned)(t) << 19))
+/* what the classifiers write: n active cells, and 1 in the vertex field of an active chunk -- the first scan then yields, per
+ * chunk, its first record slot (x) and its rank among the ACTIVE chunks (y), which indexes the second, much shorter scan */
+#define MC_CNT_FIRST(n) ((n) ? ((unsigned)(n) | 0x100u) : 0u)
 
 struct McTotals {          // written by the scan
     unsigned long long nact, nverts, ntris;
@@ -49,7 +52,8 @@ struct McEmitParams {
     const float* dist;
     const float* rgb;
     const unsigned* counts;        // per chunk packed counts
-    const uint4* base;             // per chunk exclusive prefix: x = records, y = verts, z = tris
+    const uint4* base;             // per chunk (first scan): x = records before it, y = ACTIVE chunks before it, w = packed counts
+    const uint4* abase;            // per active chunk (second scan): y = vertices, z = triangles before it
     const McRecord* recs;
     const uint4* masks;            // per active chunk: 128-bit activity mask, bit q <-> cell q of the chunk
     unsigned rec_begin, rec_end;   // records emitted by this slab (owned layers)
@@ -82,8 +86,9 @@ cudaError_t mc_launch_classify_signs(const McGrid& g, const uint4* signs, unsign
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
                            McTotals* totals, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);
-cudaError_t mc_launch_compact(const McGrid& g, const float* dist, unsigned* counts, const uint4* base,
-                              McRecord* recs, const uint4* masks, cudaStream_t s);
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+                              McRecord* recs, const uint4* masks, unsigned* acounts, cudaStream_t s);
+cudaError_t mc_launch_boundary(const uint4* base, const uint4* abase, size_t idx, void* dst_host_mapped, cudaStream_t s);
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);
 // nwords 32-bit words from device memory to MAPPED page-locked host memory, by a kernel (no copy engine involved)
 cudaError_t mc_launch_readback(const void* src_dev, void* dst_host_mapped, unsigned nwords, cudaStream_t s);
