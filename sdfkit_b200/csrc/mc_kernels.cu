@@ -728,7 +728,7 @@ __device__ static inline void st_desc(uint4* p, uint4 v)
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, unsigned n, ScanWs* ws, McTotals* totals)
+mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, unsigned n, ScanWs* ws, McTotals* totals, unsigned write_every)
 {
     __shared__ unsigned s_tile;
     __shared__ uint3 s_warp[SCAN_THREADS / 32];
@@ -802,20 +802,22 @@ mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, un
     uint3 run = make_uint3(te.x + woff.x + inc.x - sum.x, te.y + woff.y + inc.y - sum.y, te.z + woff.z + inc.z - sum.z);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (first + k < n) base[first + k] = make_uint4(run.x, run.y, run.z, c[k]);
+        // prefixes are only ever looked up for non-empty items (the lookups test the count first) and at multiples of
+        // write_every (cell-layer boundaries): 99 % of the 16-byte stores of the first scan are skipped
+        if (first + k < n && (c[k] != 0u || (first + k) % write_every == 0u)) base[first + k] = make_uint4(run.x, run.y, run.z, c[k]);
         run.x += MC_CNT_ACT(c[k]); run.y += MC_CNT_V(c[k]); run.z += MC_CNT_T(c[k]);
     }
 }
 
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
-                           McTotals* totals, cudaStream_t s)
+                           McTotals* totals, unsigned write_every, cudaStream_t s)
 {
     if (nchunks == 0) return cudaSuccess;                     // (the last tile always writes the totals otherwise)
     if (ws_bytes < mc_scan_workspace_bytes(nchunks)) return cudaErrorInvalidValue;
     cudaError_t err = cudaMemsetAsync(scan_ws, 0, mc_scan_workspace_bytes(nchunks), s);
     if (err != cudaSuccess) return err;
     const unsigned ntiles = (nchunks + SCAN_TILE - 1) / SCAN_TILE;
-    mc_scan_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(counts, base, nchunks, (ScanWs*)scan_ws, totals);
+    mc_scan_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(counts, base, nchunks, (ScanWs*)scan_ws, totals, write_every ? write_every : 1u);
     return cudaGetLastError();
 }
 
@@ -972,9 +974,9 @@ __device__ static inline int mc_find_record(const McEmitParams& p, int i, int j,
 {
     const McGrid& g = p.g;
     const unsigned chunk = ((unsigned)kl * (unsigned)g.ncy + (unsigned)j) * (unsigned)g.cpr + ((unsigned)i >> 7);
+    if (MC_CNT_ACT(__ldg(p.counts + chunk)) == 0u) return -1;      // base / masks are only written for active chunks
     const uint4 b = __ldg(p.base + chunk);
-    const uint4 m = __ldg(p.masks + chunk);       // garbage for inactive chunks: only used when the count says active
-    if (MC_CNT_ACT(b.w) == 0u) return -1;
+    const uint4 m = __ldg(p.masks + chunk);
     const unsigned q = (unsigned)i & 127u, w = q >> 5, bit = q & 31u;      // natural order: bit q of the 128-bit mask
     const unsigned ww = w == 0 ? m.x : (w == 1 ? m.y : (w == 2 ? m.z : m.w));
     if (!((ww >> bit) & 1u)) return -1;

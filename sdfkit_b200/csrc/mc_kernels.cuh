@@ -83,8 +83,9 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
 // same outputs from the sign planes written by the sampling kernels (step == 1): no pass over the distance field
 cudaError_t mc_launch_classify_signs(const McGrid& g, const uint4* signs, unsigned tiles_per_row, unsigned nzg, unsigned* counts,
                                      uint4* masks, cudaStream_t s);
+// base[i] is written only for items with a non-zero count and at multiples of write_every (1 = everywhere)
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
-                           McTotals* totals, cudaStream_t s);
+                           McTotals* totals, unsigned write_every, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
                               McRecord* recs, const uint4* masks, unsigned* acounts, cudaStream_t s);
