@@ -5,7 +5,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01s3"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01s4"
 P = os.path.join(ROOT, "profiles")
 
 
@@ -15,7 +15,7 @@ def load(name):
 
 
 d = load(tag + "_bench_1gpu.json")
-multi = {n: (load("%s_bench_%dgpu.json" % (tag, n)) or load("r01s2_bench_%dgpu.json" % n)) for n in (2, 4, 8)}
+multi = {n: (load("%s_bench_%dgpu.json" % (tag, n)) or load("r01s3_bench_%dgpu.json" % n) or load("r01s2_bench_%dgpu.json" % n)) for n in (2, 4, 8)}
 cfg = [json.loads(l) for l in open(os.path.join(P, tag + "_configs.txt")) if l.startswith("{")]
 st = d["stages_ms"]
 FP32 = 3.49e13
@@ -53,25 +53,27 @@ for n in (2, 4, 8):
 cb = d["cpu_baseline"]
 txt += """
 Weak scaling of the step: 1 → 8 GPUs = %.2f× (8-GPU line: %s). The multi-GPU e2e number is bounded by the host side of the box: 8 ranks
-streaming their shares concurrently reach ≈ 84 GB/s in total (936 MB in 11.1 ms), against 54 GB/s for one GPU alone.
+streaming their shares concurrently reach ≈ 84 GB/s in total (936 MB in 11.1 ms), against 54 GB/s for one GPU alone (the 8-GPU line is
+from the previous snapshot of the session; 1 / 2 / 4 are from this one).
 
 CPU restatement on a 256³ sample (16 cores sampling, 1 thread meshing, like the reference): %.3g voxels/s for the step
 (sampling alone %.2g voxels/s, meshing %.2g tris/s) → the 1-GPU step is ≈ %s× the CPU step, the e2e call ≈ %s×.
 
 Stage times at 1024³ on one GPU (ms): K1 sample %.2f · K2' classify (sign blocks) %.2f · K3 scan 2 × %.2f · K4a compact %.2f · K4b emit %.2f
-(triangle kernel 0.18 + vertex kernel 0.49). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 69 %%, emit
-17.5 %%, compact 5 %%, scans 4 %%, classify 3.6 %% — the same shares as the event-timed stages).
+(triangle kernel 0.19 + vertex kernel 0.44). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 71 %%, emit
+17.4 %%, compact 5.4 %%, classify 3.7 %%, scans 2 %% — the same shares as the event-timed stages).
 
 | kernel | algorithmic bytes | time | achieved | fraction of measured HBM peak |
 |---|---|---|---|---|
 | K1 `sdfk_k_sample` | 16 B × 1.07e9 voxels = 17.18 GB written (ncu: 17.31 GB DRAM writes incl. 134 MB of sign blocks, 6 MB reads) | %.2f ms | %.2f TB/s | **%.2f** |
 | K1d `sdfk_k_sample_dist` | 4 B × 1.07e9 = 4.29 GB written (ncu: 4.37 GB) | 0.90 ms | 4.8 TB/s | 0.73 (instruction-issue bound: 83 %% issue-active) |
 | K2' `mc_classify_signs` | 1 bit × 1.07e9 = 134 MB read (ncu: 146 MB) | 0.14 ms | — | replaces K2's 4.29 GB pass (0.86 ms, 0.76 of peak) |
-| K4b `mc_emit_verts` | 36 B × 3.9e6 vertices written + ≤ 4 × 8 corner reads (ncu: 1.03 GB read, 0.21 GB written) | 0.49 ms | — | latency-bound (32 %% issue-active, 28 of 32 lanes) |
+| K4b `mc_emit_verts` | 36 B × 3.9e6 vertices written + ≤ 4 × 8 corner reads (ncu: 1.0 GB read, 0.2 GB written) | 0.44 ms | — | latency-bound (≈ 32 %% issue-active, 28 of 32 lanes) |
 
 History of the round (1024³, one GPU, ms/step): first correct path 16.4 → z-column sampling + batched MC loads 7.5 → emit
 unrolled / 32-byte records 6.7 → classify counts only active cells 5.8 → lane-per-active-cell compact 5.3 → 5.2 → sign blocks
-(K2 0.86 → K2' 0.14) 4.27 → emit split into triangle + kind-sorted vertex kernels (0.93 → 0.67) and compact at 4 CTAs/SM → %.2f.
+(K2 0.86 → K2' 0.14) 4.27 → emit split into triangle + kind-sorted vertex kernels, table-driven gathers (0.93 → 0.63), compact at
+4 CTAs/SM, second scan over active chunks only (0.175 → 0.087) → %.2f.
 e2e `Sdf.ToMesh`: 64 (pageable host buffers) → 9.6 (pinned) → 7.6 (distance-only voxels) → 6.0–6.5 (z-slab pipeline, chunked emit,
 streamed downloads; 4.3 ms of it is the 234 MB over PCIe).
 
