@@ -132,9 +132,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
                 c[3 * k + 1] = r4[k].y;
                 c[3 * k + 2] = r4[k].z;
             }
-#ifndef SDFK_X_NOSIGNS
             sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
-#endif
             if (vec) {
                 if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
                 st[lane * 3 + 0] = make_float4(c[0], c[1], c[2], c[3]);
@@ -211,9 +209,6 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
         for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {   // one 32-bit sign word per lane and 8 slices
         const int zend = min(zb0 + 8, zl1);
         unsigned sacc = 0u, ssh = 0u;
-#ifdef SDFK_X_UNROLL
-#pragma unroll SDFK_X_UNROLL
-#endif
         for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
             const int iz = zl + P.z_begin;
             float d[4];
@@ -228,9 +223,7 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
                 for (int k = 0; k < 4; k++)
                     d[k] = __uint_as_float((__float_as_uint(r4[k].w) & keep[k]) | setb[k]);
             }
-#ifndef SDFK_X_NOSIGNS
             sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
-#endif
             if (vec) {
                 if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
             } else {

@@ -198,3 +198,36 @@ def test_count_all_gather_and_mesh_gather_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+@pytest.mark.parametrize("name", ["sphere", "readme", "perf", "csg50"])
+def test_packed_body_compiles_offline_and_never_adds_packed_products(name):
+    """The packed (f32x2) body: NVRTC accepts it for sm_100a without a GPU, the scalar body is left untouched, and no packed
+    add/sub ever takes a product as operand (ptxas would contract the pair into FFMA2 even under --fmad=false)."""
+    import ctypes as C
+    import re
+    from sdfkit_b200 import _native as N, scenes
+    from sdfkit_b200.exprs import PACKED_MARKER, lower
+    expr = {"sphere": scenes.sphere, "readme": scenes.readme_scene, "perf": scenes.perf_scene, "csg50": scenes.csg50}[name]()[0]
+    low = lower(expr, fast_div=lambda c: True)
+    assert "sk2_" not in low.body and low.body == lower(expr).body
+    products = set(re.findall(r"const sk_f2 (v\d+) = sk2_mul\(", low.body2))
+    for line in low.body2.splitlines():
+        m = re.match(r"\s*const sk_f2 v\d+ = sk2_(add|sub)\((\w+), (\w+)\);", line)
+        if m:
+            assert m.group(2) not in products and m.group(3) not in products, line
+    text = (low.body + PACKED_MARKER + "\n" + low.body2).encode()
+    n = C.c_size_t()
+    N.check(N.lib().sdfk_sdf_check(text, len(text), C.byref(n)))
+    assert n.value > 10000
+
+
+def test_cost_balanced_plan_weights():
+    """weighted_partition: heavier layers get thinner slabs; the e2e weight (PCIe bytes per active cell) concentrates them more."""
+    from sdfkit_b200 import dist
+    w_compute = np.ones(100) + dist.ACTIVE_CELL_COST * np.r_[np.zeros(40), np.full(20, 0.01), np.zeros(40)]
+    w_e2e = np.ones(100) + dist.ACTIVE_CELL_COST_E2E * np.r_[np.zeros(40), np.full(20, 0.01), np.zeros(40)]
+    a, b = dist.weighted_partition(w_compute, 4), dist.weighted_partition(w_e2e, 4)
+    assert a[0][0] == 0 and a[-1][1] == 100 and b[0][0] == 0 and b[-1][1] == 100
+    thick = lambda parts: [hi - lo for lo, hi in parts]
+    assert min(thick(b)) < min(thick(a)) <= 25
