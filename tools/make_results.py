@@ -52,9 +52,9 @@ for n in (2, 4, 8):
     txt += bench_row(n, multi[n])
 cb = d["cpu_baseline"]
 txt += """
-Weak scaling of the step: 1 → 8 GPUs = %.2f× (8-GPU line: %s). The multi-GPU e2e number is bounded by the host side of the box: 8 ranks
-streaming their shares concurrently reach ≈ 84 GB/s in total (936 MB in 11.1 ms), against 54 GB/s for one GPU alone (the 8-GPU line is
-from the previous snapshot of the session; 1 / 2 / 4 are from this one).
+Weak scaling of the step: 1 → 8 GPUs = %.2f× (8-GPU line: %s). The multi-GPU e2e number is bounded by the host side of the box (a
+32-vCPU, single-NUMA-node VM): 8 ranks streaming their shares concurrently reach ≈ 91 GB/s in total (937 MB in 10.3 ms), against
+55 GB/s for one GPU alone; up to 4 GPUs every rank still gets its full link (e2e 5.9–6.4 ms).
 
 CPU restatement on a 256³ sample (16 cores sampling, 1 thread meshing, like the reference): %.3g voxels/s for the step
 (sampling alone %.2g voxels/s, meshing %.2g tris/s) → the 1-GPU step is ≈ %s× the CPU step, the e2e call ≈ %s×.
