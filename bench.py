@@ -32,6 +32,11 @@ UNIT = "voxels/s"
 WEAK_GRID = {1: 1024, 2: 1280, 4: 1624, 8: 2048}       # n^3 ~= N * 1024^3 (1280 = 10 full 128-voxel chunks per row)
 
 
+def workload_name(scene, n, world):
+    """The same string in our line and in the reference arm's line: both measure this workload."""
+    return "README RepeatXY scene (%s): SdfExpr -> %d^3 Voxels (clip) + MarchingCubes, z-slab sharded over %d GPU(s)" % (scene, n, world)
+
+
 def scene_by_name(name):
     from sdfkit_b200 import scenes
     return {"readme": scenes.readme_scene, "csg50": scenes.csg50, "sphere": scenes.sphere, "perf": scenes.perf_scene}[name]()
@@ -118,7 +123,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * (d["sample_s"] + d["mesh_s"]), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "README RepeatXY scene (%s), %d^3 Voxels + MarchingCubes" % (args.scene, n), "grid": [n, n, n]},
+        "config": {"workload": workload_name(args.scene, n, args.gpus), "grid": [n, n, n]},
         "tris_per_s": tris,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": d["cores"], "kind": "port",
                          "sample": "same scene and bounds at %d^3 (1/%d of the voxels); sampling on %d threads, marching cubes "
@@ -352,7 +357,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "README RepeatXY scene (%s): SdfExpr -> %d^3 Voxels (clip) + MarchingCubes, z-slab sharded over %d GPU(s)" % (args.scene, n, world),
+            "config": {"workload": workload_name(args.scene, n, world),
                        "grid": [n, n, n], "slabs_per_rank": spr, "slab_layers": [list(l) for l in job.layers], "sdf_nodes": sdf.lowered.node_count, "sdf_flops_per_sample": sdf.lowered.flops,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (16.0 * slab_vox / 1e9),
                        "parity_mode": "IEEE f32/f64, no FMA contraction (bit-exact vs the CPU oracle)"},
@@ -386,7 +391,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", dest="n", type=int, default=0, help="grid size override (default: 1024 per GPU-equivalent)")
     ap.add_argument("--scene", default="readme")
-    ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=384, help="grid size of the bounded CPU-baseline sample (384^3: ~4 s per step on the box)")
     ap.add_argument("--slabs-per-rank", type=int, default=0, help="z-slabs dealt round-robin to every rank (default 1)")
     ap.add_argument("--uniform-slabs", action="store_true", help="equal-thickness z-slabs instead of the cost-balanced plan")
     ap.add_argument("--no-e2e", action="store_true")

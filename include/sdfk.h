@@ -170,6 +170,10 @@ int sdfk_render(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[
 int sdfk_render_depth(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3],
                       const float inv_view_proj[16], float near_plane, int iterations, int row_begin, int row_end,
                       float* depth);
+/* RayMarcher.Render followed by Vec3Data.SaveTga's pixel conversion (VectorData.cs:570-619) on the device: the rows come back
+ * as the TGA payload -- 3 bytes per pixel in B, G, R order, (byte)(v * 255) with clamping -- a quarter of the float image. */
+int sdfk_render_bgr8(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3], const float inv_view_proj[16],
+                     float near_plane, float far_plane, int iterations, int row_begin, int row_end, unsigned char* bgr);
 /* same kernels writing to device memory, asynchronous on the ctx stream */
 int sdfk_render_device(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3],
                        const float inv_view_proj[16], float near_plane, float far_plane, int iterations,

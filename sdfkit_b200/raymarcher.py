@@ -94,6 +94,18 @@ class RayMarcher:
                                     int(row_begin), int(row_end), N.fptr(out)))
         return Vec3Data(out)
 
+    def RenderTga(self, path):
+        """Render() + Vec3Data.SaveTga(path) (RayMarcher.cs:45-64, VectorData.cs:570-619) with the float -> BGR byte conversion
+        done on the device (sdfk_render_bgr8): the same file, a quarter of the device -> host traffic.  An addition to the
+        reference's surface; `Render().SaveTga(path)` writes the identical bytes."""
+        import ctypes as C
+        cam, ivp = self.camera()
+        out = N.PinnedPool.empty((self.height, self.width, 3), np.uint8)
+        N.check(N.lib().sdfk_render_bgr8(self.sdf.ctx.handle, self.sdf.handle, self.width, self.height, N.fptr(cam), N.fptr(ivp),
+                                         float(self.NearPlaneDistance), float(self.FarPlaneDistance), int(self.DepthIterations),
+                                         0, self.height, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        _write_tga(path, self.width, self.height, 2, 24, out.tobytes())
+
     def RenderDepth(self, row_begin=0, row_end=None):
         """RayMarcher.RenderDepth (RayMarcher.cs:69-93) -> FloatData."""
         row_end = self.height if row_end is None else row_end

@@ -617,3 +617,17 @@ def test_delegate_edge_cases(sk, oracle):
     assert_bits_equal(sdf(odd), oracle.eval_sdf(sdf.lowered, odd), "2049 points")
     with pytest.raises(ValueError):
         sdf(odd, np.zeros((5, 4), dtype=np.float32))
+
+
+def test_render_tga_on_device_equals_save_tga(sk, tmp_path):
+    """sdfk_render_bgr8: the TGA payload packed on the device is byte-identical to Render().SaveTga() (VectorData.cs:570-619)."""
+    from sdfkit_b200 import numerics, scenes
+    for name in ("readme", "perf"):
+        sdf = scenes_list(sk)[name][0].ToSdf()
+        rm = sk.RayMarcher(203, 77, sdf)
+        rm.ViewTransform = numerics.create_look_at(*scenes.CAMERA)
+        a, b = tmp_path / (name + "_host.tga"), tmp_path / (name + "_dev.tga")
+        rm.Render().SaveTga(str(a))
+        rm.RenderTga(str(b))
+        assert a.read_bytes() == b.read_bytes()
+        assert len(b.read_bytes()) == 18 + 203 * 77 * 3
