@@ -1264,10 +1264,42 @@ mc_emit_tris_kernel(const McEmitParams p)
     const unsigned refd = nent ? meta->refmask : 0u;                // nent == 0: "impossible case 13", emits nothing
     int* vid = s_vid[threadIdx.x];
     // ---- vertex id of every slot this cell references
+    if (i > 0 && j > 0 && kg > 0) {
+        // interior cell (nearly all): it creates slots 5, 6, 10, 12 itself, and the creator of every other edge is a fixed
+        // neighbour whose record carries the rank of that edge -- one generic loop over the referenced edges (a warp runs
+        // max-edges-per-cell iterations instead of walking 12 specialised blocks)
+        unsigned own = refd & owned;
+        while (own) {
+            const int e = __ffs((int)own) - 1;
+            own &= own - 1u;
+            vid[e] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[e] & owned));
+        }
+        // per edge e: creator offset (di | dj << 1 | dk << 2, each 0 or -1) and which rank field of its record (0: e5, 1: e6, 2: e10)
+        const unsigned long long creator = 0x882530800a2b08eull;
+        unsigned need = refd & ~owned;
+        while (need) {
+            const int e = __ffs((int)need) - 1;
+            need &= need - 1u;
+            const unsigned t = (unsigned)(creator >> (5 * e)) & 31u;
+            const int oi = i - (int)(t & 1u), oj = j - (int)((t >> 1) & 1u), okl = kl - (int)((t >> 2) & 1u);
+            unsigned cvb = 0;
+            const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl, &cvb) : -1;
+            int id = 0;
+            if (orr < 0) atomicExch(p.error_flag, 1);
+            else {
+                const McRecord* orp = p.recs + orr;
+                const uint4 oa = __ldg(reinterpret_cast<const uint4*>(orp));          // cell, info, vbase (chunk-local), tbase
+                if (MC_LEAF_NT(oa.y) == 0u) atomicExch(p.error_flag, 5);               // creator is an "impossible case 13" cell
+                else id = (int)(oa.z + cvb + MC_AUX_RANK(__ldg(&orp->aux), t >> 3));
+            }
+            vid[e] = id;
+        }
+    } else {
 #define VID(E) if ((refd >> E) & 1u) vid[E] = mc_vertex_id<E>(p, rec, meta, owned, i, j, kl, kg);
-    MC_FOR_EDGES(VID)
+        MC_FOR_EDGES(VID)
 #undef VID
-    if ((refd >> 12) & 1u) vid[12] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[12] & owned));
+        if ((refd >> 12) & 1u) vid[12] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[12] & owned));
+    }
     // ---- triangles (Cell.AddFace order): global index = id - vlocal0 + vglobal0
     {
         int* out = p.tris + ((long long)(rec.tbase - p.tlocal0)) * 3;
