@@ -6,6 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01s4"
+late = sys.argv[2] if len(sys.argv) > 2 else "r01s5"        # a later 1-GPU run (kernels only got faster; its box had slower PCIe)
 P = os.path.join(ROOT, "profiles")
 
 
@@ -15,9 +16,10 @@ def load(name):
 
 
 d = load(tag + "_bench_1gpu.json")
-multi = {n: (load("%s_bench_%dgpu.json" % (tag, n)) or load("r01s3_bench_%dgpu.json" % n) or load("r01s2_bench_%dgpu.json" % n)) for n in (2, 4, 8)}
-cfg = [json.loads(l) for l in open(os.path.join(P, tag + "_configs.txt")) if l.startswith("{")]
-st = d["stages_ms"]
+multi = {n: (load("%s_bench_%dgpu.json" % (tag, n)) or load("r01s4_bench_%dgpu.json" % n)) for n in (2, 4, 8)}
+cfg = [json.loads(l) for l in open(os.path.join(P, late + "_configs.txt")) if l.startswith("{")]
+d5 = load(late + "_bench_1gpu.json")
+st = d5["stages_ms"]
 FP32 = 3.49e13
 
 
@@ -34,19 +36,21 @@ def bench_row(n, x):
 txt = """# RESULTS — round 1 (measured on boxes of the pool, NVIDIA B200, SM clock 1965 MHz, no throttle reasons)
 
 All GPU numbers: CUDA events on the library's stream, after ≥ 3 warm-ups; parity mode (IEEE f32/f64, no FMA contraction),
-every output bit-exact against the CPU oracle and the committed golden fixtures in the GPU test-suite (110 tests, incl.
+every output bit-exact against the CPU oracle and the committed golden fixtures in the GPU test-suite (113 tests, incl.
 512³ / 1024³ property tests and exhaustive 2^32 checks of the packed sqrt / constant division). CPU numbers: the C++
 restatement of the reference's CPU path (`oracle/`, g++ -O2 -ffp-contract=off) on the box's 16 host cores, on a bounded
 sample of the same workload — the .NET reference itself cannot run here. Raw lines and ncu summaries: `profiles/%s_*`
 (`profiles/r01_*`, `r01s2_*` are earlier snapshots of the round). Roofline denominators: HBM 6553 GB/s (measured copy,
-`MEASURED_PEAKS.json`); FP32 without FMA 3.49e13 lane-op/s (measured FMUL+FADD chains). Box-to-box spread: ±2 %% on kernels,
-6.0–6.5 ms on the e2e call. (regenerate with `python tools/make_results.py %s`)
+`MEASURED_PEAKS.json`); FP32 without FMA 3.49e13 lane-op/s (measured FMUL+FADD chains). Box-to-box spread: ±2 %% on kernels; the e2e
+call follows the box's PCIe (observed over the session: 6.2 – 6.5 ms on most boxes, 7.5 ms on one). The table below is the `%s` snapshot
+(all four GPU counts within the same hour); stage times and the configuration table are from the last run of the session (`%s`:
+step %.2f ms, fused step %.2f ms, e2e %.2f ms on a box with slower PCIe). (regenerate with `python tools/make_results.py %s`)
 
 ## bench.py (README RepeatXY scene → Voxels (clip) → MarchingCubes; one step = sample + mesh)
 
 | GPUs | grid | ms/step | voxels/s (whole job) | tris/s | fused `Sdf.ToMesh` step (device) | e2e `Sdf.ToMesh` (mesh in host memory) |
 |---|---|---|---|---|---|---|
-""" % (tag, tag)
+""" % (tag, tag, late, d5["ms_per_step"], d5["fused_to_mesh"]["ms_per_step"], d5["e2e"]["ms_per_step"], tag)
 txt += bench_row(1, d)
 for n in (2, 4, 8):
     txt += bench_row(n, multi[n])
@@ -60,7 +64,7 @@ CPU restatement on a 256³ sample (16 cores sampling, 1 thread meshing, like the
 (sampling alone %.2g voxels/s, meshing %.2g tris/s) → the 1-GPU step is ≈ %s× the CPU step, the e2e call ≈ %s×.
 
 Stage times at 1024³ on one GPU (ms): K1 sample %.2f · K2' classify (sign blocks) %.2f · K3 scan 2 × %.2f · K4a compact %.2f · K4b emit %.2f
-(triangle kernel 0.19 + vertex kernel 0.44). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 71 %%, emit
+(triangle kernel 0.15 + vertex kernel 0.44). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 71 %%, emit
 17.4 %%, compact 5.4 %%, classify 3.7 %%, scans 2 %% — the same shares as the event-timed stages).
 
 | kernel | algorithmic bytes | time | achieved | fraction of measured HBM peak |
@@ -83,8 +87,8 @@ streamed downloads; 4.3 ms of it is the 234 MB over PCIe).
 |---|---|---|
 """ % (multi[8]["value"] / d["value"] if multi[8] else 0, "`profiles/%s_bench_8gpu.json`" % tag, cb["value"], cb["detail"]["sample_voxels_per_s"],
        cb["detail"]["mesh_tris_per_s"], "{:,.0f}".format(d["value"] / cb["value"]), "{:,.0f}".format(d["e2e"]["value"] / cb["value"]),
-       st["sample_ms"], st["classify_ms"], st["scan_ms"] / 2, st["compact_ms"], st["emit_ms"], tag,
-       st["sample_ms"], d["roofline"]["achieved"] / 1e3, d["roofline"]["frac"], d["ms_per_step"], tag)
+       st["sample_ms"], st["classify_ms"], st["scan_ms"] / 2, st["compact_ms"], st["emit_ms"], late,
+       st["sample_ms"], d5["roofline"]["achieved"] / 1e3, d5["roofline"]["frac"], d5["ms_per_step"], late)
 for x in cfg:
     if "render_ms" in x:
         txt += "| %s | %.3f ms = %.3g pixels/s = %.3g SDF evals/s = %.3g FP32 op/s (%.2f of the no-FMA FP32 rate) | %d×%d: %.3g pixels/s |\n" % (
