@@ -64,8 +64,8 @@ CPU restatement on a 256³ sample (16 cores sampling, 1 thread meshing, like the
 (sampling alone %.2g voxels/s, meshing %.2g tris/s) → the 1-GPU step is ≈ %s× the CPU step, the e2e call ≈ %s×.
 
 Stage times at 1024³ on one GPU (ms): K1 sample %.2f · K2' classify (sign blocks) %.2f · K3 scan 2 × %.2f · K4a compact %.2f · K4b emit %.2f
-(triangle kernel 0.15 + vertex kernel 0.44). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 71 %%, emit
-17.4 %%, compact 5.4 %%, classify 3.7 %%, scans 2 %% — the same shares as the event-timed stages).
+(triangle kernel 0.15 + vertex kernel 0.44). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 72 %%, emit
+16.4 %%, compact 5.4 %%, classify 3.7 %%, scans 2 %% — the same shares as the event-timed stages).
 
 | kernel | algorithmic bytes | time | achieved | fraction of measured HBM peak |
 |---|---|---|---|---|
