@@ -17,3 +17,11 @@ def oracle():
     import oracle as orc
     orc.build()
     return orc
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """libsdfk.so is built in-tree (git-ignored); from a clean checkout build it once, like __graft_entry__.build() does.
+    (A no-op when the library is newer than its sources.  The product itself never builds or falls back on its own.)"""
+    from sdfkit_b200 import build
+    build.build()
