@@ -14,9 +14,41 @@ from . import numerics
 class Mesh:
     """SdfKit.Mesh (Mesh.cs): Vertices / Colors / Normals (n x 3 float32), Triangles (flat int32, 3 per triangle)."""
 
-    def __init__(self, vertices, colors, normals, triangles, vmin, vmax):
+    def __init__(self, vertices, colors, normals, triangles, vmin=None, vmax=None):
+        """Mesh(vertices, colors, normals, triangles) (Mesh.cs:21-28); Min/Max are measured unless the caller already has them."""
         self.Vertices, self.Colors, self.Normals, self.Triangles = vertices, colors, normals, triangles
         self.Min, self.Max = vmin, vmax
+        if vmin is None or vmax is None:
+            self._measure()
+
+    def _measure(self):
+        """Mesh.Measure (Mesh.cs:30-45)."""
+        if len(self.Vertices) > 0:
+            v = np.asarray(self.Vertices, dtype=np.float32).reshape(-1, 3)
+            self.Min, self.Max = v.min(axis=0).astype(np.float32), v.max(axis=0).astype(np.float32)
+        elif self.Min is None:
+            self.Min = self.Max = np.zeros(3, dtype=np.float32)
+
+    def Transform(self, transform):
+        """Mesh.Transform (Mesh.cs:47-64) on the host arrays, in the reference's float32 operation order: v' = v . M (row
+        vector), n' = normalize(n . transpose(inverse(M with its translation cleared))).  (MarchingCubes.CreateMesh's own
+        index -> world transform is applied on the device, inside the emit kernel.)"""
+        f = np.float32
+        M = np.asarray(transform, dtype=f).reshape(4, 4)
+        nt = M.copy()
+        nt[3, 0] = nt[3, 1] = nt[3, 2] = f(0.0)
+        nt[3, 3] = f(1.0)
+        inv = numerics.invert(nt)
+        Nm = numerics.transpose(inv) if inv is not None else np.full((4, 4), np.nan, dtype=f)
+        v = np.array(self.Vertices, dtype=f).reshape(-1, 3)
+        n = np.array(self.Normals, dtype=f).reshape(-1, 3)
+        with np.errstate(all="ignore"):
+            tv = np.stack([((v[:, 0] * M[0, k] + v[:, 1] * M[1, k]) + v[:, 2] * M[2, k]) + M[3, k] for k in range(3)], axis=1).astype(f)
+            tn = np.stack([(n[:, 0] * Nm[0, k] + n[:, 1] * Nm[1, k]) + n[:, 2] * Nm[2, k] for k in range(3)], axis=1).astype(f)
+            ln = np.sqrt((tn[:, 0] * tn[:, 0] + tn[:, 1] * tn[:, 1]) + tn[:, 2] * tn[:, 2]).astype(f)
+            tn = (tn / ln[:, None]).astype(f)
+        self.Vertices, self.Normals = tv, tn
+        self._measure()
 
     @property
     def Center(self):

@@ -631,3 +631,22 @@ def test_render_tga_on_device_equals_save_tga(sk, tmp_path):
         rm.RenderTga(str(b))
         assert a.read_bytes() == b.read_bytes()
         assert len(b.read_bytes()) == 18 + 203 * 77 * 3
+
+
+def test_host_mesh_transform_equals_the_fused_device_transform(sk):
+    """Mesh.Transform (Mesh.cs:47-64) applied on the host to an index-space mesh gives, bit for bit, the mesh whose transform was
+    fused into the emit kernel (MarchingCubes.cs:85-90)."""
+    from sdfkit_b200 import numerics, scenes
+    expr, mn, mx = scenes.perf_scene()
+    vox = expr.ToSdf().ToVoxels(mn, mx, 50, 37, 29)
+    world = vox.ToMesh()
+    gm = sk.MarchingCubes.CreateGpuMesh(vox, transform=False)
+    index_space = gm.download()
+    M, _ = numerics.mesh_transforms(vox.Min, vox.Max, vox.NX, vox.NY, vox.NZ)
+    index_space.Transform(M)
+    assert_bits_equal(index_space.Vertices, world.Vertices, "host-transformed vertices")
+    assert_bits_equal(index_space.Normals, world.Normals, "host-transformed normals")
+    assert_bits_equal(index_space.Min, world.Min, "aabb min")
+    assert_bits_equal(index_space.Max, world.Max, "aabb max")
+    f = expr.ToSdfFunc()                                            # SdfExprEx.ToSdfFunc: one point at a time
+    assert f((0.1, 0.2, 0.3)).shape == (4,)

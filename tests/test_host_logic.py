@@ -231,3 +231,44 @@ def test_cost_balanced_plan_weights():
     assert a[0][0] == 0 and a[-1][1] == 100 and b[0][0] == 0 and b[-1][1] == 100
     thick = lambda parts: [hi - lo for lo, hi in parts]
     assert min(thick(b)) < min(thick(a)) <= 25
+
+
+def test_mirror_covers_the_reference_api_surface():
+    """Every public member of the reference's hot-path types (tests/golden/reference_api_surface.json, extracted from the C#
+    sources by tests/golden/make_api_surface.py) exists under the same name in the Python mirror."""
+    import json
+    import os
+    import sdfkit_b200 as sk
+    surf = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_api_surface.json")))
+    where = {"SdfConfig": [sk.SdfConfig], "SdfEx": [sk.GpuSdf], "SdfExprs": [sk.SdfExprs], "SdfExprEx": [sk.SdfExpr],
+             "SdfIndexedInput": [sk.SdfIndexedInput], "Voxels": [sk.Voxels], "MarchingCubes": [sk.MarchingCubes], "Mesh": [sk.Mesh],
+             "RayMarcher": [sk.RayMarcher]}
+    instance_attrs = {"Voxels": {"Colors", "Values", "DX", "DY", "DZ", "NX", "NY", "NZ", "Min", "Max"},
+                      "Mesh": {"Vertices", "Colors", "Normals", "Triangles", "Min", "Max"},
+                      "SdfIndexedInput": {"Position", "Index"},
+                      "RayMarcher": {"DepthIterations", "FarPlaneDistance", "NearPlaneDistance", "VerticalFieldOfViewDegrees", "ViewTransform"}}
+    missing = []
+    for typ, info in surf.items():
+        for name in info["members"]:
+            if name == "this[]":
+                name = "__getitem__"
+            if name in instance_attrs.get(typ, ()):
+                continue                      # set per instance in __init__ (checked on real objects by the GPU tests)
+            if not any(hasattr(c, name) for c in where[typ]):
+                missing.append("%s.%s" % (typ, name))
+    assert not missing, missing
+
+
+def test_mesh_transform_and_measure():
+    """Mesh.Transform / Measure (Mesh.cs:30-64) on host arrays: row-vector convention, normals by the inverse transpose."""
+    import sdfkit_b200 as sk
+    from sdfkit_b200 import numerics
+    v = np.float32([[0, 0, 0], [1, 0, 0], [0, 2, 0]])
+    n = np.float32([[0, 0, 1], [0, 0, 1], [1, 0, 0]])
+    m = sk.Mesh(v.copy(), np.ones_like(v), n.copy(), np.int32([0, 1, 2]))
+    assert np.array_equal(m.Min, [0, 0, 0]) and np.array_equal(m.Max, [1, 2, 0])
+    M = numerics.multiply(numerics.create_scale(2, 3, 4), numerics.create_translation(10, 20, 30))
+    m.Transform(M)
+    assert np.allclose(m.Vertices, [[10, 20, 30], [12, 20, 30], [10, 26, 30]])
+    assert np.allclose(m.Normals, [[0, 0, 1], [0, 0, 1], [1, 0, 0]])
+    assert np.allclose(m.Min, [10, 20, 30]) and np.allclose(m.Max, [12, 26, 30]) and np.allclose(m.Center, [11, 23, 30])
