@@ -44,6 +44,11 @@ namespace SdfKit.B200
         [DllImport(Lib)] public static extern int sdfk_ctx_set_option(IntPtr ctx, int option, int value);
         [DllImport(Lib)] public static extern int sdfk_mesh_destroy(IntPtr mesh);
 
+        // Not bound here (not needed by the single-process drop-in; see include/sdfk.h): instrumentation (sdfk_ctx_mark / _elapsed /
+        // _timer_* / _launch_count / _stream / _create_on_stream, sdfk_mesh_stats, sdfk_sdf_check), the multi-GPU slab API
+        // (sdfk_voxels_sample_slab / _sample_distances / _resample / _info, sdfk_mesh_classify / _emit / _emit_host /
+        // _device_ptrs, sdfk_render_device), pinned-buffer helpers (sdfk_host_alloc / _free), the packed-evaluator self-tests
+        // (sdfk_constdiv_verify, sdfk_selftest_sqrt) and sdfk_render_bgr8 (TGA payload packed on the device).
         [DllImport(Lib)] public static extern int sdfk_render(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos, float* invViewProj,
             float near, float far, int iterations, int rowBegin, int rowEnd, float* rgb);
         [DllImport(Lib)] public static extern int sdfk_render_depth(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos,
