@@ -192,11 +192,27 @@ def transform_point(v, m):
     return out
 
 
+_camera_cache = {}
+
+
 def camera_matrices(view, width, height, fov_degrees, near, far):
     """The matrix part of RayMarcher.GetCameraRays (RayMarcher.cs:95-108).
 
-    Returns (camera_position[3], inverse(view * projection)[4,4]) as float32.
+    Returns (camera_position[3], inverse(view * projection)[4,4]) as float32.  (Memoised like mesh_transforms.)
     """
+    view = np.asarray(view, dtype=np.float32).reshape(4, 4)
+    key = (view.tobytes(), int(width), int(height), float(fov_degrees), float(near), float(far))
+    hit = _camera_cache.get(key)
+    if hit is not None:
+        return hit[0].copy(), hit[1].copy()
+    cam_pos, ivp = _camera_matrices(view, width, height, fov_degrees, near, far)
+    if len(_camera_cache) > 256:
+        _camera_cache.clear()
+    _camera_cache[key] = (cam_pos.copy(), ivp.copy())
+    return cam_pos, ivp
+
+
+def _camera_matrices(view, width, height, fov_degrees, near, far):
     view = np.asarray(view, dtype=np.float32).reshape(4, 4)
     cam_t = invert(view)
     if cam_t is None:
@@ -212,9 +228,26 @@ def camera_matrices(view, width, height, fov_degrees, near, far):
     return cam_pos, ivp
 
 
+_mesh_transform_cache = {}
+
+
 def mesh_transforms(vmin, vmax, nx, ny, nz):
     """Index-space -> world transform of MarchingCubes.CreateMesh (MarchingCubes.cs:85-90) and the
-    normal transform Mesh.Transform derives from it (Mesh.cs:49-55).  Returns (M, N) float32 4x4."""
+    normal transform Mesh.Transform derives from it (Mesh.cs:49-55).  Returns (M, N) float32 4x4.
+    (Memoised: the scalar float32 emulation below costs ~0.3 ms, 5 % of a 1024^3 Sdf.ToMesh call.)"""
+    vmin, vmax = vec3(vmin), vec3(vmax)
+    key = (vmin.tobytes(), vmax.tobytes(), int(nx), int(ny), int(nz))
+    hit = _mesh_transform_cache.get(key)
+    if hit is not None:
+        return hit[0].copy(), hit[1].copy()
+    m, n = _mesh_transforms(vmin, vmax, nx, ny, nz)
+    if len(_mesh_transform_cache) > 256:
+        _mesh_transform_cache.clear()
+    _mesh_transform_cache[key] = (m.copy(), n.copy())
+    return m, n
+
+
+def _mesh_transforms(vmin, vmax, nx, ny, nz):
     vmin, vmax = vec3(vmin), vec3(vmax)
     size = (vmax - vmin).astype(np.float32)
     center = ((vmin + vmax).astype(np.float32) * f32(0.5)).astype(np.float32)
