@@ -7,6 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01s4"
 late = sys.argv[2] if len(sys.argv) > 2 else "r01s5"        # a later 1-GPU run (kernels only got faster; its box had slower PCIe)
+last = load("r01s6_bench_1gpu.json")                          # the very last bench.py run of the session
 P = os.path.join(ROOT, "profiles")
 
 
@@ -44,13 +45,15 @@ sample of the same workload — the .NET reference itself cannot run here. Raw l
 `MEASURED_PEAKS.json`); FP32 without FMA 3.49e13 lane-op/s (measured FMUL+FADD chains). Box-to-box spread: ±2 %% on kernels; the e2e
 call follows the box's PCIe (observed over the session: 6.2 – 6.5 ms on most boxes, 7.5 ms on one). The table below is the `%s` snapshot
 (all four GPU counts within the same hour); stage times and the configuration table are from the last run of the session (`%s`:
-step %.2f ms, fused step %.2f ms, e2e %.2f ms on a box with slower PCIe). (regenerate with `python tools/make_results.py %s`)
+step %.2f ms, fused step %.2f ms, e2e %.2f ms on a box with slower PCIe). The last `bench.py` run of the session (`r01s6`, all changes
+in): step %.2f ms = %.3g voxels/s, fused step %.2f ms, e2e %.2f ms = %.3g voxels/s, K1 at %.2f of the HBM peak. (regenerate with `python tools/make_results.py %s`)
 
 ## bench.py (README RepeatXY scene → Voxels (clip) → MarchingCubes; one step = sample + mesh)
 
 | GPUs | grid | ms/step | voxels/s (whole job) | tris/s | fused `Sdf.ToMesh` step (device) | e2e `Sdf.ToMesh` (mesh in host memory) |
 |---|---|---|---|---|---|---|
-""" % (tag, tag, late, d5["ms_per_step"], d5["fused_to_mesh"]["ms_per_step"], d5["e2e"]["ms_per_step"], tag)
+""" % (tag, tag, late, d5["ms_per_step"], d5["fused_to_mesh"]["ms_per_step"], d5["e2e"]["ms_per_step"],
+       last["ms_per_step"], last["value"], last["fused_to_mesh"]["ms_per_step"], last["e2e"]["ms_per_step"], last["e2e"]["value"], last["roofline"]["frac"], tag)
 txt += bench_row(1, d)
 for n in (2, 4, 8):
     txt += bench_row(n, multi[n])
