@@ -7,7 +7,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01s4"
 late = sys.argv[2] if len(sys.argv) > 2 else "r01s5"        # a later 1-GPU run (kernels only got faster; its box had slower PCIe)
-last = load("r01s6_bench_1gpu.json")                          # the very last bench.py run of the session
 P = os.path.join(ROOT, "profiles")
 
 
@@ -17,6 +16,7 @@ def load(name):
 
 
 d = load(tag + "_bench_1gpu.json")
+last = load("r01s6_bench_1gpu.json")                          # the very last bench.py run of the session
 multi = {n: (load("%s_bench_%dgpu.json" % (tag, n)) or load("r01s4_bench_%dgpu.json" % n)) for n in (2, 4, 8)}
 cfg = [json.loads(l) for l in open(os.path.join(P, late + "_configs.txt")) if l.startswith("{")]
 d5 = load(late + "_bench_1gpu.json")
