@@ -167,6 +167,45 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
     }
 }
 
+// One block of up to 8 z slices of a column for sdfk_k_sample_dist: evaluates, stores the distances, returns the lane's sign
+// word.  WALLS = false: no slice of the block lies on a z wall and the row is not a wall row.
+template <bool WALLS>
+static __device__ __forceinline__ unsigned sdfk_sample_dist_block(const sdfk_sample_params& P, float* __restrict__ dist, size_t& vbase,
+                                                                  size_t plane, int zb0, int zend, const float* px, float py,
+                                                                  const unsigned* keep, const unsigned* setb, bool rowwall, bool vec,
+                                                                  int x0, unsigned lane)
+{
+    unsigned sacc = 0u, ssh = 0u;
+    for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
+        const int iz = zl + P.z_begin;
+        float d[4];
+        if (WALLS && (rowwall || (P.clip && (iz == 0 || iz == P.nz - 1)))) {      // warp-uniform
+            d[0] = d[1] = d[2] = d[3] = P.clip_value;
+        } else {
+            const float pz = P.m2 + (float)iz * P.dz;
+            sk_float4 r4[4];
+            sdf_eval2(sk_make3(px[0], py, pz), sk_make3(px[1], py, pz), r4[0], r4[1]);     // two voxels per call (packed f32x2 when enabled)
+            sdf_eval2(sk_make3(px[2], py, pz), sk_make3(px[3], py, pz), r4[2], r4[3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                d[k] = __uint_as_float((__float_as_uint(r4[k].w) & keep[k]) | setb[k]);
+        }
+        sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
+        if (vec) {
+            if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (x0 + k < P.nx) {
+                    const size_t v = vbase + lane * 4u + k;
+                    dist[v] = d[k];
+                }
+            }
+        }
+    }
+    return sacc;
+}
+
 // Distance-only variant of K1 for Sdf.ToMesh (SdfKit/Sdf.cs:59-63), where the caller never sees the voxels: 4 B/voxel
 // instead of 16; the colours marching cubes needs (two corners per created vertex) are evaluated afterwards by
 // sdfk_k_vertex_colors.  Same traversal and arithmetic as sdfk_k_sample.
@@ -208,34 +247,11 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
         uint4 sw = make_uint4(0u, 0u, 0u, 0u);
         for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {   // one 32-bit sign word per lane and 8 slices
         const int zend = min(zb0 + 8, zl1);
-        unsigned sacc = 0u, ssh = 0u;
-        for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
-            const int iz = zl + P.z_begin;
-            float d[4];
-            if (rowwall || (P.clip && (iz == 0 || iz == P.nz - 1))) {      // warp-uniform
-                d[0] = d[1] = d[2] = d[3] = P.clip_value;
-            } else {
-                const float pz = P.m2 + (float)iz * P.dz;
-                sk_float4 r4[4];
-                sdf_eval2(sk_make3(px[0], py, pz), sk_make3(px[1], py, pz), r4[0], r4[1]);     // two voxels per call: packed f32x2
-                sdf_eval2(sk_make3(px[2], py, pz), sk_make3(px[3], py, pz), r4[2], r4[3]);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    d[k] = __uint_as_float((__float_as_uint(r4[k].w) & keep[k]) | setb[k]);
-            }
-            sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
-            if (vec) {
-                if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (x0 + k < P.nx) {
-                        const size_t v = vbase + lane * 4u + k;
-                        dist[v] = d[k];
-                    }
-                }
-            }
-        }
+        // only the first / last 8-slice block of the grid (z walls) and the two wall rows need the ClipToBounds logic per slice:
+        // every other block runs the lean instance of the loop (13 instructions less per 128 voxels of an issue-bound kernel)
+        const bool walls = rowwall || (P.clip && (zb0 + P.z_begin == 0 || zend + P.z_begin == P.nz));
+        const unsigned sacc = walls ? sdfk_sample_dist_block<true>(P, dist, vbase, plane, zb0, zend, px, py, keep, setb, rowwall, vec, x0, lane)
+                                    : sdfk_sample_dist_block<false>(P, dist, vbase, plane, zb0, zend, px, py, keep, setb, rowwall, vec, x0, lane);
         const int sq = (zb0 >> 3) & 3;
         if (sq == 0) sw.x = sacc; else if (sq == 1) sw.y = sacc; else if (sq == 2) sw.z = sacc; else sw.w = sacc;
         }
