@@ -12,6 +12,9 @@
 // face/interior tests, centre vertex), vertex positions, normals and colour renders are
 // "parity unpinned" by the reference -- for them this file (a line-by-line restatement of
 // MarchingCubes.cs / Cell.cs / RayMarcher.cs) is the only authority.
+// A second, independent restatement written during the survey agrees with this one on every count it
+// recorded (tests/golden/reference_known_answers.json "survey_probe", tests/test_golden_fixtures.py), including the triangle
+// count of a white-noise field that reaches 68 decision leaves of the ambiguous cases -- the only independent pin there.
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -- no FMA contraction, like RyuJIT).
 //
