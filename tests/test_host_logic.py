@@ -272,3 +272,27 @@ def test_mesh_transform_and_measure():
     assert np.allclose(m.Vertices, [[10, 20, 30], [12, 20, 30], [10, 26, 30]])
     assert np.allclose(m.Normals, [[0, 0, 1], [0, 0, 1], [1, 0, 0]])
     assert np.allclose(m.Min, [10, 20, 30]) and np.allclose(m.Max, [12, 26, 30]) and np.allclose(m.Center, [11, 23, 30])
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on host cores) runs without a GPU and prints exactly one JSON line
+    with the keys the contract names; `workload` is the same string our arm prints for that grid / GPU count."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-n", "48"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "voxel_samples_per_s" and d["unit"] == "voxels/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"]["workload"] == bench.workload_name("readme", 1024, 1)
