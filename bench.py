@@ -112,6 +112,36 @@ def cpu_baseline(scene_name, n_sample, steps, warmup):
         "sample_s": ts, "mesh_s": tm, "cores": cores}
 
 
+def cpu_baseline_expr(expr, mn, mx, n):
+    """cpu_baseline for an arbitrary SdfExpr (one pass, no warm-up): the CPU leg of tools/run_configs.py's table."""
+    import numpy as np
+    import oracle
+    cores = os.cpu_count() or 1
+    sdf = oracle.compile_sdf(expr.Lower())
+    mn, mx = np.float32(mn), np.float32(mx)
+    t0 = time.perf_counter()
+    v, c = oracle.sample(sdf, mn, mx, n, n, n, threads=cores)
+    t1 = time.perf_counter()
+    oracle.clip(v, mn, mx)
+    m = oracle.marching_cubes(v, c, mn, mx)
+    t2 = time.perf_counter()
+    return {"cpu_grid": n, "cpu_cores": cores, "cpu_samples_per_s": n ** 3 / (t1 - t0), "cpu_tris_per_s": len(m.triangles) / (t2 - t1),
+            "cpu_cells_per_s": (n - 1) ** 3 / (t2 - t1), "cpu_step_voxels_per_s": n ** 3 / (t2 - t0), "cpu_triangles": len(m.triangles)}
+
+
+def cpu_baseline_render(expr, w, h):
+    """The CPU restatement of RayMarcher.Render (row bands on all cores, RayMarcher.cs:50-61) on a w x h image."""
+    import oracle
+    from sdfkit_b200 import numerics, scenes
+    cores = os.cpu_count() or 1
+    sdf = oracle.compile_sdf(expr.Lower())
+    view = numerics.create_look_at(*scenes.CAMERA)
+    t0 = time.perf_counter()
+    oracle.render(sdf, w, h, view=view, bands=cores)
+    t = time.perf_counter() - t0
+    return {"cpu_image": [w, h], "cpu_cores": cores, "cpu_render_ms": t * 1e3, "cpu_pixels_per_s": w * h / t}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

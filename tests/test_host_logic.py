@@ -296,3 +296,19 @@ def test_bench_reference_arm_prints_one_contract_line():
     sys.path.insert(0, root)
     import bench
     assert d["config"]["workload"] == bench.workload_name("readme", 1024, 1)
+
+
+def test_only_the_allowed_places_touch_the_oracle():
+    """The oracle is test infrastructure: outside tests/ only __graft_entry__ (build + smoke) and bench.py (cpu_baseline /
+    --impl reference legs) may import it -- not the product package, not the tools."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("sdfkit_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for fn in files:
+                if fn.endswith(".py"):
+                    text = open(os.path.join(dirpath, fn)).read()
+                    if re.search(r"^\s*(import oracle|from oracle)", text, re.M):
+                        offenders.append(os.path.join(sub, fn))
+    assert not offenders, offenders

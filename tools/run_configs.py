@@ -60,18 +60,9 @@ def gpu_mesh_config(sk, skd, ctx, name, expr, mn, mx, n, reps):
 
 
 def cpu_mesh_config(expr, mn, mx, n):
-    import oracle
-    cores = os.cpu_count() or 1
-    sdf = oracle.compile_sdf(expr.Lower())
-    mn, mx = np.float32(mn), np.float32(mx)
-    t0 = time.perf_counter()
-    v, c = oracle.sample(sdf, mn, mx, n, n, n, threads=cores)
-    t1 = time.perf_counter()
-    oracle.clip(v, mn, mx)
-    m = oracle.marching_cubes(v, c, mn, mx)
-    t2 = time.perf_counter()
-    return {"cpu_grid": n, "cpu_cores": cores, "cpu_samples_per_s": n ** 3 / (t1 - t0), "cpu_tris_per_s": len(m.triangles) / (t2 - t1),
-            "cpu_cells_per_s": (n - 1) ** 3 / (t2 - t1), "cpu_step_voxels_per_s": n ** 3 / (t2 - t0), "cpu_triangles": len(m.triangles)}
+    """CPU column of the table: bench.py's cpu_baseline leg (the only code outside tests/ that may run the oracle)."""
+    import bench
+    return bench.cpu_baseline_expr(expr, mn, mx, n)
 
 
 def gpu_render_config(sk, ctx, name, expr, w, h, reps):
@@ -104,15 +95,8 @@ def gpu_render_config(sk, ctx, name, expr, w, h, reps):
 
 
 def cpu_render_config(expr, w, h):
-    import oracle
-    from sdfkit_b200 import numerics, scenes
-    cores = os.cpu_count() or 1
-    sdf = oracle.compile_sdf(expr.Lower())
-    view = numerics.create_look_at(*scenes.CAMERA)
-    t0 = time.perf_counter()
-    oracle.render(sdf, w, h, view=view, bands=cores)
-    t = time.perf_counter() - t0
-    return {"cpu_image": [w, h], "cpu_cores": cores, "cpu_render_ms": t * 1e3, "cpu_pixels_per_s": w * h / t}
+    import bench
+    return bench.cpu_baseline_render(expr, w, h)
 
 
 FP32_SRC = r"""
