@@ -11,8 +11,9 @@
  *     last failure on the calling thread.  No C++ exception crosses this boundary.
  *   - the caller owns every host buffer it passes; the library never keeps a host pointer after return.
  *   - handles are released only by their *_destroy function.
- *   - all entry points taking a ctx are serialised per ctx (internal mutex); one ctx drives one GPU
- *     (one process per GPU; a multi-GPU job shards by z-slab / row band).
+ *   - all entry points taking a ctx are serialised per ctx (internal mutex).  sdfk_ctx_create drives one GPU;
+ *     sdfk_ctx_create_multi drives N GPUs from one process: sampling / meshing shard by z-slab, rendering by row band,
+ *     behind the same entry points (see "multi-GPU" below and DESIGN.md section 5).
  *   - matrices are 16 floats, row-major System.Numerics.Matrix4x4 (M11 M12 M13 M14 M21 ...), row-vector
  *     convention; the caller computes them (the C# shim with System.Numerics itself).
  *   - device layout of voxels is x-fastest; the C# `[x,y,z]` layout appears only in import/export.
@@ -49,6 +50,31 @@ int sdfk_version(void);
 int sdfk_ctx_create(int device, sdfk_ctx** out);
 /* same, launching on a caller-owned cudaStream_t (e.g. the host framework's current stream) */
 int sdfk_ctx_create_on_stream(int device, void* cuda_stream, sdfk_ctx** out);
+/* ---- multi-GPU context: N devices of one box behind ONE handle -------------------------
+ * devices = NULL means 0..ndev-1; a device may be listed more than once (every entry gets its own stream, pools and
+ * worker thread -- used by the single-GPU tests of this layer).  On such a context
+ *   sdfk_sdf_compile        loads the module on every device;
+ *   sdfk_voxels_sample      returns voxels SHARDED by z-slab (cost-balanced cuts, one halo slice per side, recomputed
+ *                           rather than exchanged); sdfk_voxels_resample / _clip / _export / _destroy understand them;
+ *   sdfk_mesh_create        on sharded voxels (step 1) classifies every slab on its device, exchanges the per-slab
+ *                           (vertices, triangles) counts in host memory and emits at global ids: a device-resident mesh
+ *                           in one part per device; sdfk_mesh_counts / _export / _stats / _destroy understand it,
+ *                           sdfk_mesh_export moves every part over its own PCIe link;
+ *   sdfk_sdf_to_mesh_host   (SdfEx.ToMesh, Sdf.cs:59-63) lands ONE host mesh, every device copying its share to its
+ *                           global offset;
+ *   sdfk_render*            render row bands (RayMarcher.cs:50-61), one per device, into the one host image;
+ *   the timers / marks      report the slowest device, sdfk_ctx_launch_count the sum.
+ * Slab-level calls (sdfk_voxels_sample_slab / _distances, sdfk_mesh_classify / _emit, sdfk_voxels_import, sdfk_sdf_eval)
+ * run on device 0 of the context.  The results are identical, bit for bit and in order, to a single-GPU context's. */
+int sdfk_ctx_create_multi(int ndev, const int* devices, sdfk_ctx** out);
+int sdfk_ctx_device_count(sdfk_ctx* ctx, int* ndev);
+/* host wall clock (ms) of the last multi-GPU call on this context, from entry until every device had finished */
+int sdfk_ctx_last_wall_ms(sdfk_ctx* ctx, double* milliseconds);
+/* The z-slab plan: cuts the cell layers of an nx*ny*nz grid (MarchingCubes.cs:49-68) into `parts` contiguous ranges of
+ * near-equal cost = voxels + active_cell_cost * active cells, the active cells estimated by a coarse (<= 128^3) meshing
+ * pass of the same SDF (0 = default cost).  kb_ke receives 2*parts ints: [kb, ke) per part.  Deterministic. */
+int sdfk_plan_layers(sdfk_ctx* ctx, sdfk_sdf* sdf, const float min[3], const float max[3], int nx, int ny, int nz, int step,
+                     int clip, int parts, double active_cell_cost, int* kb_ke);
 int sdfk_ctx_destroy(sdfk_ctx* ctx);
 int sdfk_ctx_synchronize(sdfk_ctx* ctx);
 int sdfk_ctx_stream(sdfk_ctx* ctx, void** cuda_stream);
@@ -110,12 +136,17 @@ int sdfk_voxels_resample(sdfk_voxels* vox, sdfk_sdf* sdf, int clip);
 int sdfk_voxels_import(sdfk_ctx* ctx, const float* values, const float* colors, const float min[3],
                        const float max[3], int nx, int ny, int nz, sdfk_voxels** out);
 /* Voxels.Values / Voxels.Colors (Voxels.cs:8-9) in C# layout; either pointer may be NULL.  For a slab the
- * arrays are [nx][ny][z_end - z_begin].                                                                 */
+ * arrays are [nx][ny][z_end - z_begin].  The field leaves in x-chunks: a chunk is transposed to the C# layout on the
+ * device while the previous one crosses PCIe (page-locked destinations -- sdfk_host_alloc -- travel at link speed).   */
 int sdfk_voxels_export(sdfk_voxels* vox, float* values, float* colors);
 /* Voxels.ClipToBounds (Voxels.cs:133-167) on resident voxels */
 int sdfk_voxels_clip(sdfk_voxels* vox);
 /* dims = {nx, ny, nz, z_begin, z_end}; device pointers to the x-fastest arrays (dist, rgb) */
 int sdfk_voxels_info(sdfk_voxels* vox, int dims[5], void** dist_dev, void** rgb_dev);
+/* sharded voxels (multi-GPU context): the cell layers [kb, ke) every device owns (2 ints per part), and the per-device
+ * slab handle (borrowed; NULL for a device that owns nothing) */
+int sdfk_voxels_layers(sdfk_voxels* vox, int* kb_ke, int max_parts, int* nparts);
+int sdfk_voxels_part(sdfk_voxels* vox, int part, sdfk_voxels** out);
 int sdfk_voxels_destroy(sdfk_voxels* vox);
 
 /* ---- MarchingCubes.CreateMesh / Voxels.ToMesh (MarchingCubes.cs:39-92, Voxels.cs:67-70) -------------
@@ -156,6 +187,9 @@ int sdfk_mesh_host_ptrs(sdfk_mesh* mesh, const float** vertices, const float** c
 int sdfk_mesh_export(sdfk_mesh* mesh, float* vertices, float* colors, float* normals, int32_t* triangles,
                      float aabb[6]);
 int sdfk_mesh_device_ptrs(sdfk_mesh* mesh, void** vertices, void** colors, void** normals, void** triangles);
+/* sharded mesh (multi-GPU context): part r (borrowed handle on device r; NULL if empty) and the global index of its first
+ * vertex / triangle */
+int sdfk_mesh_part(sdfk_mesh* mesh, int part, sdfk_mesh** out, int64_t* vertex_base, int64_t* triangle_base);
 /* stats[0..3] = device ms of classify, scan, compact, emit; stats[4] = active cells; stats[7] = 1 if classified from sign planes */
 int sdfk_mesh_stats(sdfk_mesh* mesh, double stats[8]);
 int sdfk_mesh_destroy(sdfk_mesh* mesh);
@@ -174,6 +208,12 @@ int sdfk_render_depth(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float ca
  * as the TGA payload -- 3 bytes per pixel in B, G, R order, (byte)(v * 255) with clamping -- a quarter of the float image. */
 int sdfk_render_bgr8(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3], const float inv_view_proj[16],
                      float near_plane, float far_plane, int iterations, int row_begin, int row_end, unsigned char* bgr);
+/* RayMarcher.RenderDepth followed by FloatData.SaveDepthTga's pixel conversion (VectorData.cs:244-276) on the device: the rows
+ * come back as the TGA payload, one byte per pixel: v >= tga_far -> 0, v <= tga_near -> 255, else
+ * (byte)(255.0f * (tga_far - v) / (tga_far - tga_near)).  march_near = RayMarcher.NearPlaneDistance. */
+int sdfk_render_depth_gray8(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3], const float inv_view_proj[16],
+                            float march_near, int iterations, float tga_near, float tga_far, int row_begin, int row_end,
+                            unsigned char* gray);
 /* same kernels writing to device memory, asynchronous on the ctx stream */
 int sdfk_render_device(sdfk_ctx* ctx, sdfk_sdf* sdf, int w, int h, const float cam_pos[3],
                        const float inv_view_proj[16], float near_plane, float far_plane, int iterations,

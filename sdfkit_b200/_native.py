@@ -19,6 +19,10 @@ SIGNATURES = {
     "sdfk_version": (C.c_int, []),
     "sdfk_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "sdfk_ctx_create_on_stream": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "sdfk_ctx_create_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]),
+    "sdfk_ctx_device_count": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "sdfk_ctx_last_wall_ms": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "sdfk_plan_layers": (C.c_int, [_vp, _vp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int)]),
     "sdfk_ctx_destroy": (C.c_int, [_vp]),
     "sdfk_ctx_synchronize": (C.c_int, [_vp]),
     "sdfk_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -46,6 +50,8 @@ SIGNATURES = {
     "sdfk_voxels_export": (C.c_int, [_vp, _fp, _fp]),
     "sdfk_voxels_clip": (C.c_int, [_vp]),
     "sdfk_voxels_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sdfk_voxels_layers": (C.c_int, [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "sdfk_voxels_part": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "sdfk_voxels_destroy": (C.c_int, [_vp]),
     "sdfk_mesh_create": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _fp, _fp, PROGRESS_FN, _vp, C.POINTER(_vp)]),
     "sdfk_mesh_classify": (C.c_int, [_vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _i64p, _i64p]),
@@ -57,12 +63,15 @@ SIGNATURES = {
     "sdfk_mesh_host_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "sdfk_mesh_export": (C.c_int, [_vp, _fp, _fp, _fp, C.POINTER(C.c_int32), _fp]),
     "sdfk_mesh_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sdfk_mesh_part": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _i64p, _i64p]),
     "sdfk_mesh_stats": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "sdfk_mesh_destroy": (C.c_int, [_vp]),
     "sdfk_render": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "sdfk_render_depth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "sdfk_render_bgr8": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_ubyte)]),
+    "sdfk_render_depth_gray8": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                          C.POINTER(C.c_ubyte)]),
     "sdfk_render_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, _vp]),
 }
 
@@ -151,19 +160,39 @@ OPT_SIGN_PLANES = 1
 
 
 class Context:
-    """sdfk_ctx: one GPU + one stream.  `default()` gives the per-process context (LOCAL_RANK aware)."""
+    """sdfk_ctx: one GPU + one stream, or -- Context(devices=[0, 1, ...]) -- N GPUs of one box behind one handle
+    (sdfk_ctx_create_multi: z-slab / row-band sharding inside the library).  `default()` gives the per-process context
+    (LOCAL_RANK aware)."""
     _default = None
 
-    def __init__(self, device=None, stream=None):
-        if device is None:
-            device = int(os.environ.get("LOCAL_RANK", "0"))
+    def __init__(self, device=None, stream=None, devices=None):
         h = _vp()
-        if stream is None:
-            check(lib().sdfk_ctx_create(int(device), C.byref(h)))
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            arr = (C.c_int * len(devices))(*devices)
+            check(lib().sdfk_ctx_create_multi(len(devices), arr, C.byref(h)))
+            device = devices[0]
         else:
-            check(lib().sdfk_ctx_create_on_stream(int(device), _vp(int(stream)), C.byref(h)))
+            if device is None:
+                device = int(os.environ.get("LOCAL_RANK", "0"))
+            if stream is None:
+                check(lib().sdfk_ctx_create(int(device), C.byref(h)))
+            else:
+                check(lib().sdfk_ctx_create_on_stream(int(device), _vp(int(stream)), C.byref(h)))
         self.handle = h
         self.device = int(device)
+        self.devices = devices or [int(device)]
+
+    def device_count(self):
+        n = C.c_int()
+        check(lib().sdfk_ctx_device_count(self.handle, C.byref(n)))
+        return n.value
+
+    def last_wall_ms(self):
+        """Host wall clock of the last multi-GPU library call on this context (entry until every device had finished)."""
+        ms = C.c_double()
+        check(lib().sdfk_ctx_last_wall_ms(self.handle, C.byref(ms)))
+        return ms.value
 
     @classmethod
     def default(cls):

@@ -1439,3 +1439,23 @@ cudaError_t mc_launch_readback(const void* src_dev, void* dst_host_mapped, unsig
     mc_readback_kernel<<<1, 32, 0, s>>>((const unsigned*)src_dev, (unsigned*)dst_host_mapped, nwords);
     return cudaGetLastError();
 }
+
+// (records, vertices, triangles) before the first chunk of every cell layer l = 0..nlayers-1, to mapped host memory
+// (the slab planner reads per-layer triangle counts of its coarse probe pass from these)
+__global__ void mc_layer_prefix_kernel(const uint4* __restrict__ base, const uint4* __restrict__ abase, size_t per_layer, unsigned nlayers,
+                                       uint4* __restrict__ dst)
+{
+    for (unsigned l = blockIdx.x * blockDim.x + threadIdx.x; l < nlayers; l += gridDim.x * blockDim.x) {
+        const uint4 b = base[per_layer * l];
+        const uint4 a = abase[b.y];
+        dst[l] = make_uint4(b.x, a.y, a.z, 0u);
+    }
+    __threadfence_system();
+}
+
+cudaError_t mc_launch_layer_prefixes(const uint4* base, const uint4* abase, size_t per_layer, unsigned nlayers, void* dst_host_mapped, cudaStream_t s)
+{
+    if (nlayers == 0) return cudaSuccess;
+    mc_layer_prefix_kernel<<<1, 128, 0, s>>>(base, abase, per_layer, nlayers, (uint4*)dst_host_mapped);
+    return cudaGetLastError();
+}

@@ -90,6 +90,8 @@ size_t mc_scan_workspace_bytes(unsigned nchunks);
 cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
                               McRecord* recs, const uint4* masks, unsigned* acounts, cudaStream_t s);
 cudaError_t mc_launch_boundary(const uint4* base, const uint4* abase, size_t idx, void* dst_host_mapped, cudaStream_t s);
+// the same prefixes at the first chunk of each of nlayers cell layers (per_layer chunks apart): nlayers uint4 to mapped host memory
+cudaError_t mc_launch_layer_prefixes(const uint4* base, const uint4* abase, size_t per_layer, unsigned nlayers, void* dst_host_mapped, cudaStream_t s);
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s);
 // nwords 32-bit words from device memory to MAPPED page-locked host memory, by a kernel (no copy engine involved)
 cudaError_t mc_launch_readback(const void* src_dev, void* dst_host_mapped, unsigned nwords, cudaStream_t s);

@@ -67,33 +67,14 @@ def plan_layers(sdf, vmin, vmax, nx, ny, nz, parts, step=1, clip=True, coarse=12
     """Cut the cell layers into `parts` contiguous slabs of near-equal COST instead of equal thickness.  A z-slab job is
     as slow as its busiest rank, and the surface of a scene is rarely spread evenly in z (the README scene fills 18 % of
     the layers).  The per-layer work is estimated from a coarse meshing pass of the same SDF on this GPU (every rank
-    computes the same plan; nothing is exchanged): cost(layer) = voxels(layer) + ACTIVE_CELL_COST * active_cells(layer)."""
-    ncz = cells_along(nz, step)
-    if parts <= 1 or ncz <= parts:
-        return partition(ncz, parts)
-    c = int(min(coarse, nz))
-    if c < 8:
-        return partition(ncz, parts)
-    cx, cy = max(8, int(round(nx * c / nz))), max(8, int(round(ny * c / nz)))
-    probe = SlabMesher(sdf, vmin, vmax, cx, cy, c, 0, cells_along(c, 1), clip, 0.0, 1)
-    try:
-        probe.sample()
-        nv, nt = probe.classify()
-        probe.M = probe.Nn = None                 # index space: vertex z = coarse layer coordinate
-        N.check(N.lib().sdfk_mesh_emit(probe.mesh.handle, 0, 0, None, None))
-        mesh = probe.mesh.download(pinned=False)
-    finally:
-        probe.close()
-    tri_per_layer = np.zeros(c, dtype=np.float64)
-    if len(mesh.Triangles):
-        z = mesh.Vertices[mesh.Triangles.reshape(-1, 3)[:, 0], 2]
-        np.add.at(tri_per_layer, np.clip(z.astype(np.int64), 0, c - 1), 1.0)
-    # a coarse layer covers nz/c fine layers; active cells scale with the square of the refinement, ~2 triangles per cell
-    scale = (nz / c)
-    fine_layer = np.minimum((np.arange(ncz) * step * c) // nz, c - 1)
-    active = 0.5 * tri_per_layer[fine_layer] * scale * step
-    weights = float(nx) * ny * step + float(active_cell_cost) * active
-    return weighted_partition(weights, parts)
+    computes the same plan; nothing is exchanged): cost(layer) = voxels(layer) + ACTIVE_CELL_COST * active_cells(layer).
+    One implementation for every host: sdfk_plan_layers (csrc/sdfk_multi.inl), which the multi-GPU context also uses."""
+    sdf = require_gpu_sdf(sdf)
+    vmin, vmax = numerics.vec3(vmin), numerics.vec3(vmax)
+    out = (C.c_int * (2 * int(parts)))()
+    N.check(N.lib().sdfk_plan_layers(sdf.ctx.handle, sdf.handle, N.fptr(vmin), N.fptr(vmax), int(nx), int(ny), int(nz), int(step),
+                                     1 if clip else 0, int(parts), float(active_cell_cost), out))
+    return [(out[2 * k], out[2 * k + 1]) for k in range(int(parts))]
 
 
 def slab_slices(kb, ke, step, nz):

@@ -115,3 +115,19 @@ class RayMarcher:
                                           N.fptr(ivp), float(self.NearPlaneDistance), int(self.DepthIterations),
                                           int(row_begin), int(row_end), N.fptr(out)))
         return FloatData(out)
+
+    def RenderDepthGray(self, near, far, row_begin=0, row_end=None):
+        """RenderDepth() followed by FloatData.SaveDepthTga's pixel conversion (VectorData.cs:262-273) on the device
+        (sdfk_render_depth_gray8): the TGA payload, one byte per pixel -- a quarter of the device -> host traffic."""
+        import ctypes as C
+        row_end = self.height if row_end is None else row_end
+        cam, ivp = self.camera()
+        out = N.PinnedPool.empty((row_end - row_begin, self.width), np.uint8)
+        N.check(N.lib().sdfk_render_depth_gray8(self.sdf.ctx.handle, self.sdf.handle, self.width, self.height, N.fptr(cam), N.fptr(ivp),
+                                                float(self.NearPlaneDistance), int(self.DepthIterations), float(near), float(far),
+                                                int(row_begin), int(row_end), out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return out
+
+    def RenderDepthTga(self, path, near, far):
+        """RenderDepth().SaveDepthTga(path, near, far) with the byte conversion on the device: the identical file."""
+        _write_tga(path, self.width, self.height, 3, 8, self.RenderDepthGray(near, far).tobytes())

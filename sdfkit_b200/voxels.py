@@ -91,8 +91,14 @@ def _net_float(x):
     if np.isinf(x):
         return "Infinity" if x > 0 else "-Infinity"
     s = np.format_float_positional(x, unique=True, trim="-")
-    if x != 0 and (abs(float(x)) >= 1e15 or abs(float(x)) < 1e-5):
-        s = np.format_float_scientific(x, unique=True, trim="-", exp_digits=2).replace("e", "E")
+    if x != 0:
+        # single precision: scientific notation when the decimal exponent is below -4 or at least max(#digits, 7)
+        # (5e-5f -> "5E-05", 1e7f -> "1E+07", 12345678f -> "12345678"; double's thresholds are -5 and 15)
+        sci = np.format_float_scientific(x, unique=True, trim="-", exp_digits=2)
+        mant, exp = sci.split("e")
+        e10, ndig = int(exp), len(mant.replace("-", "").replace(".", ""))
+        if e10 < -4 or e10 >= max(ndig, 7):
+            s = mant + "E" + exp
     return "-0" if (s == "0" and np.signbit(x)) else s
 
 
@@ -163,6 +169,7 @@ class Voxels:
         self.ctx = ctx or N.Context.default()
         self.handle = None
         self._values = self._colors = None
+        self._dirty = False          # the host copy was written through the indexers and not yet re-imported
         if len(args) == 4:                                   # Voxels(float[,,] values, Vector3[,,] colors, min, max)
             values, colors, vmin, vmax = args
             values = N.f32c(values)
@@ -235,7 +242,9 @@ class Voxels:
             self.handle, other.handle = other.handle, None
         else:
             N.check(N.lib().sdfk_voxels_resample(self.handle, sdf.handle, 1 if clip else 0))
+        self._sdf = sdf                                    # distance-only voxels: the SDF supplies vertex colours at meshing time
         self._values = self._colors = None
+        self._dirty = False
 
     def ClipToBounds(self):
         self._ensure()
@@ -243,42 +252,83 @@ class Voxels:
         self._values = None
 
     def _ensure(self):
-        if self.handle is None:   # an empty Voxels(min,max,n..): zeros
+        """The device copy exists and is current: an empty Voxels(min, max, n..) uploads zeros, host writes made through
+        the indexers (the reference's Values is live storage, Voxels.cs:42-64) are re-imported."""
+        if self.handle is None:
             z = np.zeros((self.NX, self.NY, self.NZ), dtype=np.float32)
             h = C.c_void_p()
             N.check(N.lib().sdfk_voxels_import(self.ctx.handle, N.fptr(z), None, N.fptr(self.Min), N.fptr(self.Max),
                                                self.NX, self.NY, self.NZ, C.byref(h)))
             self.handle = h
+        elif self._dirty:
+            values, colors = self._values, self._host_colors()
+            h = C.c_void_p()
+            N.check(N.lib().sdfk_voxels_import(self.ctx.handle, N.fptr(values), N.fptr(colors), N.fptr(self.Min), N.fptr(self.Max),
+                                               self.NX, self.NY, self.NZ, C.byref(h)))
+            N.lib().sdfk_voxels_destroy(self.handle)
+            self.handle = h
+            self._dirty = False
 
-    # ---- host materialisation (C# layout)
+    def _export(self, want_colors):
+        shape = (self.NX, self.NY, self.NZ, 3) if want_colors else (self.NX, self.NY, self.NZ)
+        out = N.PinnedPool.empty(shape, np.float32)        # page-locked: the chunked export runs at PCIe speed
+        N.check(N.lib().sdfk_voxels_export(self.handle, None if want_colors else N.fptr(out), N.fptr(out) if want_colors else None))
+        return out
+
+    def _host_colors(self):
+        if self._colors is None:
+            try:
+                self._colors = self._export(True)
+            except N.SdfkError as e:                       # distance-only voxels hold no colours: the reference's zeros
+                if e.code != -4:
+                    raise
+                self._colors = np.zeros((self.NX, self.NY, self.NZ, 3), dtype=np.float32)
+        return self._colors
+
+    # ---- host materialisation (C# layout).  The arrays are read-only snapshots: writes go through the indexers
+    # (`voxels[ix, iy, iz] = d`), which keep the device copy in step; `voxels.Values[...] = d` raises instead of silently
+    # meshing the unmodified field.
     @property
     def Values(self):
         if self._values is None:
             self._ensure()
-            out = np.empty((self.NX, self.NY, self.NZ), dtype=np.float32)
-            N.check(N.lib().sdfk_voxels_export(self.handle, N.fptr(out), None))
-            self._values = out
-        return self._values
+            self._values = self._export(False)
+        v = self._values.view()
+        v.setflags(write=False)
+        return v
 
     @property
     def Colors(self):
-        if self._colors is None:
+        if self.handle is None:
             self._ensure()
-            out = np.empty((self.NX, self.NY, self.NZ, 3), dtype=np.float32)
-            N.check(N.lib().sdfk_voxels_export(self.handle, None, N.fptr(out)))
-            self._colors = out
-        return self._colors
+        c = self._host_colors().view()
+        c.setflags(write=False)
+        return c
 
-    def __getitem__(self, idx):
-        """voxels[ix, iy, iz] (Voxels.cs:42-46) or voxels[Vector3 p] -- the voxel containing point p (Voxels.cs:48-56)."""
+    def _index(self, idx):
         if len(idx) == 3 and all(isinstance(k, (int, np.integer)) for k in idx):
-            ix, iy, iz = idx
+            ix, iy, iz = (int(k) for k in idx)
         else:
             p = numerics.vec3(idx)
             ix = int((p[0] - self.Min[0]) / self.DX)
             iy = int((p[1] - self.Min[1]) / self.DY)
             iz = int((p[2] - self.Min[2]) / self.DZ)
+        if not (0 <= ix < self.NX and 0 <= iy < self.NY and 0 <= iz < self.NZ):
+            raise IndexError("voxel index (%d, %d, %d) outside %dx%dx%d" % (ix, iy, iz, self.NX, self.NY, self.NZ))   # IndexOutOfRangeException
+        return ix, iy, iz
+
+    def __getitem__(self, idx):
+        """voxels[ix, iy, iz] (Voxels.cs:42-46) or voxels[Vector3 p] -- the voxel containing point p (Voxels.cs:48-56)."""
+        ix, iy, iz = self._index(idx)
         return self.Values[ix, iy, iz]
+
+    def __setitem__(self, idx, value):
+        """The indexers' setters (Voxels.cs:44-45,57-63): writes the host copy; the device copy is refreshed before the next
+        ClipToBounds / ToMesh."""
+        ix, iy, iz = self._index(idx)
+        self.Values                                        # materialise
+        self._values[ix, iy, iz] = np.float32(value)
+        self._dirty = True
 
     # ---- meshing
     def ToMesh(self, isoValue=0.0, step=1, progress=None):

@@ -276,7 +276,8 @@ def test_mesh_transform_and_measure():
 
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU restatement timed on host cores) runs without a GPU and prints exactly one JSON line
-    with the keys the contract names; `workload` is the same string our arm prints for that grid / GPU count."""
+    with the keys the contract names.  The labels are honest: `config` names the grid that was really measured (a bounded
+    sample), `sample_of` the workload it stands for, `same_config` says they differ, `warmup` is what was really done."""
     import json
     import subprocess
     import sys
@@ -295,7 +296,11 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     sys.path.insert(0, root)
     import bench
-    assert d["config"]["workload"] == bench.workload_name("readme", 1024, 1)
+    assert d["config"]["grid"] == [48, 48, 48] and "48^3" in d["config"]["workload"] and "1024" not in d["config"]["workload"]
+    assert d["config"]["same_config"] is False
+    assert d["config"]["sample_of"]["workload"] == bench.workload_name("readme", 1024, 1) and d["config"]["sample_of"]["grid"] == [1024] * 3
+    assert d["warmup"] == 0 and d["steps"] == 1 and d["cpu_baseline"]["detail"]["grid"] == [48, 48, 48]
+    assert abs(d["config"]["sample_of"]["voxel_fraction"] - (48 / 1024) ** 3) < 1e-12
 
 
 def test_only_the_allowed_places_touch_the_oracle():
