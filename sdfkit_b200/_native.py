@@ -126,6 +126,7 @@ class PinnedPool:
     """Page-locked host buffers for exports (sdfk_host_alloc), recycled when every numpy view of a buffer has been
     garbage collected -- pinning 100s of MB costs far more than copying them, so buffers are never freed eagerly."""
     _free = {}      # size class -> [pointer, ...]
+    _seen = set()   # size classes that have been allocated before
 
     class _Block:
         def __init__(self, ptr, size):
@@ -143,13 +144,18 @@ class PinnedPool:
         dtype = np.dtype(dtype)
         nbytes = int(np.prod(shape)) * dtype.itemsize
         size = 1 << max(12, (max(nbytes, 1) - 1).bit_length())
-        lst = cls._free.get(size)
+        lst = cls._free.setdefault(size, [])
         if lst:
             ptr = lst.pop()
         else:
-            p = _vp()
-            check(lib().sdfk_host_alloc(size, C.byref(p)))
-            ptr = p.value
+            # `img = sdf.ToImage(...)` in a loop holds the previous result while the next one is made: the first miss of a
+            # size class pins two buffers (pinning costs ~0.5 ms/MB), so the second call already finds a recycled one
+            for _ in range(2 if (size <= (256 << 20) and size not in cls._seen) else 1):
+                p = _vp()
+                check(lib().sdfk_host_alloc(size, C.byref(p)))
+                lst.append(p.value)
+            cls._seen.add(size)
+            ptr = lst.pop()
         block = cls._Block(ptr, size)
         buf = (C.c_ubyte * size).from_address(ptr)
         buf._block = block                       # the ctypes buffer keeps the block alive; numpy keeps the buffer alive

@@ -299,9 +299,10 @@ class Voxels:
 
     @property
     def Colors(self):
-        if self.handle is None:
+        if self._colors is None:
             self._ensure()
-        c = self._host_colors().view()
+            self._colors = self._export(True)              # distance-only voxels: SdfkError ("hold no colours")
+        c = self._colors.view()
         c.setflags(write=False)
         return c
 
