@@ -354,11 +354,36 @@ def export_record(sk, ctx, sdf, mn, mx):
 # ------------------------------------------------------------------------------------------------
 # strong scaling through the multi-GPU context of the C ABI (one process, N devices)
 # ------------------------------------------------------------------------------------------------
+def pcie_aggregate(ndevs):
+    """Device -> page-locked host copy rate with 1, 2, 4, .. devices copying AT THE SAME TIME (256 MB each, best of 3): what the
+    host side of the box can absorb -- the ceiling of any e2e number that lands a result in host memory."""
+    import torch
+    out = {}
+    nb = 1 << 28
+    for nd in ndevs:
+        src = [torch.empty(nb, dtype=torch.uint8, device="cuda:%d" % d) for d in range(nd)]
+        dst = [torch.empty(nb, dtype=torch.uint8, pin_memory=True) for _ in range(nd)]
+        best = 1e9
+        for _ in range(4):
+            for d in range(nd):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            for d in range(nd):
+                with torch.cuda.device(d):
+                    dst[d].copy_(src[d], non_blocking=True)
+            for d in range(nd):
+                torch.cuda.synchronize(d)
+            best = min(best, time.perf_counter() - t0)
+        out[str(nd)] = nd * nb / best / 1e9
+        del src, dst
+    return out
+
+
 def strong_record(sk, expr, mn, mx, n, ndevs, steps, single_mesh_sha, scene):
     """The same n^3 job on 1, 2, 4, .. devices behind sdfk_ctx_create_multi: (a) device-resident step = sharded Voxels
     (16 B/voxel) + MarchingCubes, (b) e2e = Sdf.ToMesh landing ONE host mesh.  Wall clock from call to completion on all
     devices (+ the slowest device's own event span); every result is compared with the single-GPU digest."""
-    out = {"grid": [n, n, n], "scene": scene, "by_devices": {},
+    out = {"grid": [n, n, n], "scene": scene, "by_devices": {}, "pcie_d2h_aggregate_gbs": pcie_aggregate(ndevs),
            "note": "strong scaling: total work fixed; one process drives all devices through the C ABI (sdfk_ctx_create_multi), slabs cut by "
                    "the cost-balanced planner, counts exchanged in host memory, every device copies its share of the mesh to its offset of "
                    "one host result over its own PCIe link"}
@@ -740,6 +765,9 @@ def parity_check(sk, skd, dist, torch, ctx, sdf, job, allc, offs, expr, mn, mx, 
     # (a) gather the shares to rank 0 over NVLink, slab by slab in global order (slab g belongs to rank g % world)
     spr = job.spr
     per_slab = counts.transpose(1, 0, 2).reshape(world * spr, 2)
+    # (NCCL sets its point-to-point channels up on first use: one small untimed exchange first)
+    skd.gather_rows(torch.zeros((4, 3), dtype=torch.float32, device=dev), [4] * world, dst=0)
+    skd.gather_rows(torch.zeros((4, 3), dtype=torch.int32, device=dev), [4] * world, dst=0)
     gathered = [[], [], [], []]
     torch.cuda.synchronize()
     dist.barrier()

@@ -123,8 +123,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
             float d[4];
             float c[12];
             sk_float4 r4[4];
-            sdf_eval2(sk_make3(px[0], py, pz), sk_make3(px[1], py, pz), r4[0], r4[1]);     // two voxels per call: packed f32x2
-            sdf_eval2(sk_make3(px[2], py, pz), sk_make3(px[3], py, pz), r4[2], r4[3]);
+            sdf_eval_grid(px, py, pz, r4);                          // the lane's 4 voxels of this row at once: shared y/z work and range guards
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 d[k] = (zwall || xywall[k]) ? P.clip_value : r4[k].w;
@@ -184,8 +183,7 @@ static __device__ __forceinline__ unsigned sdfk_sample_dist_block(const sdfk_sam
         } else {
             const float pz = P.m2 + (float)iz * P.dz;
             sk_float4 r4[4];
-            sdf_eval2(sk_make3(px[0], py, pz), sk_make3(px[1], py, pz), r4[0], r4[1]);     // two voxels per call (packed f32x2 when enabled)
-            sdf_eval2(sk_make3(px[2], py, pz), sk_make3(px[3], py, pz), r4[2], r4[3]);
+            sdf_eval_grid(px, py, pz, r4);                          // the lane's 4 voxels of this row at once: shared y/z work and range guards
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 d[k] = __uint_as_float((__float_as_uint(r4[k].w) & keep[k]) | setb[k]);
@@ -248,7 +246,9 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
         for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {   // one 32-bit sign word per lane and 8 slices
         const int zend = min(zb0 + 8, zl1);
         // only the first / last 8-slice block of the grid (z walls) and the two wall rows need the ClipToBounds logic per slice:
-        // every other block runs the lean instance of the loop (13 instructions less per 128 voxels of an issue-bound kernel)
+        // every other block runs the lean instance of the loop (13 instructions less per 128 voxels of an issue-bound kernel).
+        // (Measured and dropped: a fully unrolled 8-slice block -- slower for every scene, 2x for large bodies; moving the
+        // x-wall masks into the wall instance -- no gain.)
         const bool walls = rowwall || (P.clip && (zb0 + P.z_begin == 0 || zend + P.z_begin == P.nz));
         const unsigned sacc = walls ? sdfk_sample_dist_block<true>(P, dist, vbase, plane, zb0, zend, px, py, keep, setb, rowwall, vec, x0, lane)
                                     : sdfk_sample_dist_block<false>(P, dist, vbase, plane, zb0, zend, px, py, keep, setb, rowwall, vec, x0, lane);
@@ -411,16 +411,24 @@ sdfk_k_render(const sdfk_render_params P, float* __restrict__ rgb)
         const sk_float3 rb = sdfk_ray_dir(P, (int)(pb % P.w), P.row_begin + (int)(pb / P.w));
         float da = P.nearp - 0.1f, db = P.nearp - 0.1f;            // RayMarcher.cs:136
         float ca[3] = {0.0f, 0.0f, 0.0f}, cb[3] = {0.0f, 0.0f, 0.0f};
-        for (int it = 0; it < P.iters; it++) {                     // fixed count, no early out (RayMarcher.cs:138-145)
+        // fixed count, no early out (RayMarcher.cs:138-145).  Only the LAST sample's colour is kept (RayMarcher.cs:143-144), so
+        // the last iteration is peeled: in the loop the colour outputs are dead and the compiler drops everything that only
+        // feeds them (for the README scene two of the four divisions per evaluation).
+        for (int it = 0; it + 1 < P.iters; it++) {
             sk_float4 s0, s1;
             sdf_eval2(sk_make3(ra.x * da + P.cam[0], ra.y * da + P.cam[1], ra.z * da + P.cam[2]),
                       sk_make3(rb.x * db + P.cam[0], rb.y * db + P.cam[1], rb.z * db + P.cam[2]), s0, s1);
             da = da + s0.w;
             db = db + s1.w;
-            if (it == P.iters - 1) {
-                ca[0] = ca[0] + s0.x; ca[1] = ca[1] + s0.y; ca[2] = ca[2] + s0.z;
-                cb[0] = cb[0] + s1.x; cb[1] = cb[1] + s1.y; cb[2] = cb[2] + s1.z;
-            }
+        }
+        if (P.iters > 0) {
+            sk_float4 s0, s1;
+            sdf_eval2(sk_make3(ra.x * da + P.cam[0], ra.y * da + P.cam[1], ra.z * da + P.cam[2]),
+                      sk_make3(rb.x * db + P.cam[0], rb.y * db + P.cam[1], rb.z * db + P.cam[2]), s0, s1);
+            da = da + s0.w;
+            db = db + s1.w;
+            ca[0] = ca[0] + s0.x; ca[1] = ca[1] + s0.y; ca[2] = ca[2] + s0.z;
+            cb[0] = cb[0] + s1.x; cb[1] = cb[1] + s1.y; cb[2] = cb[2] + s1.z;
         }
         const float ax = P.cam[0] + ra.x * da, ay = P.cam[1] + ra.y * da, az = P.cam[2] + ra.z * da;
         const float bx = P.cam[0] + rb.x * db, by = P.cam[1] + rb.y * db, bz = P.cam[2] + rb.z * db;

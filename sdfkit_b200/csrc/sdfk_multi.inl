@@ -225,6 +225,14 @@ static int plan_layers_native(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
     if (parts <= 1 || ncz <= parts) { uniform_partition(ncz, parts, out); return SDFK_OK; }
     const int cz = std::min(128, nz);
     if (cz < 8) { uniform_partition(ncz, parts, out); return SDFK_OK; }
+    sdfk_sdf::PlanKey key;
+    memset(&key, 0, sizeof(key));
+    memcpy(key.mn, mn, 12); memcpy(key.mx, mx, 12);
+    key.nx = nx; key.ny = ny; key.nz = nz; key.step = step; key.clip = clip ? 1 : 0; key.parts = parts; key.cost = active_cell_cost;
+    static const bool use_cache = getenv("SDFK_NO_PLAN_CACHE") == nullptr;
+    if (use_cache)
+        for (auto& e : s->plans)
+            if (memcmp(&e.first, &key, sizeof(key)) == 0) { out = e.second; return SDFK_OK; }
     const int cx = std::max(8, (int)std::lround((double)nx * cz / nz)), cy = std::max(8, (int)std::lround((double)ny * cz / nz));
     const int nkc = cells_along(cz, 1);
     std::vector<double> tri_per_layer((size_t)cz, 0.0);
@@ -265,6 +273,8 @@ static int plan_layers_native(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
         w[(size_t)k] = (double)nx * ny * step + active_cell_cost * active;
     }
     weighted_partition(w, parts, out);
+    if (s->plans.size() >= 16) s->plans.erase(s->plans.begin());
+    s->plans.emplace_back(key, out);
     return SDFK_OK;
 }
 

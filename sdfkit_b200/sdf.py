@@ -40,10 +40,22 @@ class GpuSdf:
         # (README ToImage 0.189 -> 0.236 ms, CSG-50 sampling 10.8 -> 16.5 ms: register pairs, per-half traffic), so it is off
         # by default; DESIGN.md section 2b.
         import os
-        from .exprs import PACKED_MARKER
+        from .exprs import GRID_MARKER, PACKED_MARKER
         packed = os.environ.get("SDFK_PACKED", "0") == "1"
-        self.lowered = lower(expr, fast_div=self.ctx.constdiv_ok if packed else None)
-        body = (self.lowered.body + ((PACKED_MARKER + "\n" + self.lowered.body2) if packed else "")).encode()
+        plain = os.environ.get("SDFK_PLAIN_BODY", "0") == "1"        # debugging: only the scalar body, the library's default device forms
+        # Division by a constant may use the 3-instruction correctly rounded sequence once the device has compared it with
+        # div.rn.f32 for all 2^32 dividends (ctx.constdiv_ok: a few ms per constant, cached per context).
+        self.lowered = lower(expr, fast_div=None if plain else self.ctx.constdiv_ok, packed=packed)
+        low = self.lowered
+        if plain:
+            text = low.body
+        elif packed:
+            text = low.body + PACKED_MARKER + "\n" + low.body2
+        else:
+            # the scalar body (what the oracle compiles) + the device forms: two-point evaluator and row-of-voxels evaluator with
+            # shared range guards (exprs._emit_multi) -- same IEEE operations, bit-identical results
+            text = low.body + PACKED_MARKER + "\n" + low.pair_body + GRID_MARKER + "\n" + low.grid_text
+        body = text.encode()
         h = C.c_void_p()
         N.check(N.lib().sdfk_sdf_compile(self.ctx.handle, body, len(body), C.byref(h)))
         self.handle = h

@@ -529,6 +529,33 @@ def test_chunked_emit_to_host_equals_single_gpu(sk, oracle, nslabs, chunks, colo
 
 # ---------------------------------------------------------------------------------------------- packed (f32x2) evaluator
 
+@pytest.mark.parametrize("name,dims", [("sphere", (33, 20, 17)), ("readme", (64, 64, 64)), ("perf", (50, 37, 29)), ("csg50", (96, 96, 48))])
+def test_default_device_forms_equal_plain_scalar_body(sk, oracle, monkeypatch, name, dims):
+    """The shared-guard device forms (default) and the plain scalar body (SDFK_PLAIN_BODY=1: what a host that only sends the
+    scalar body gets) give identical voxels, meshes and images -- and both equal the oracle (other tests)."""
+    from sdfkit_b200 import numerics, scenes
+    expr, mn, mx = scenes_list(sk)[name]
+    nx, ny, nz = dims
+    res = []
+    for plain in ("0", "1"):
+        monkeypatch.setenv("SDFK_PLAIN_BODY", plain)
+        sdf = expr.ToSdf()
+        vox = sdf.ToVoxels(mn, mx, nx, ny, nz)
+        mesh = sdf.ToMesh(mn, mx, nx, ny, nz)
+        img = sdf.ToImage(97, 55, *scenes.CAMERA)
+        pts = np.random.default_rng(11).uniform(-4, 4, (5001, 3)).astype(np.float32)
+        pts[:7] = [[0, 0, 0], [1.125, 0, 0], [-0.0, 0.0, -0.0], [1e-30, 0, 0], [3e38, 0, 0], [np.inf, 0, 0], [np.nan, 1, 1]]
+        res.append((vox.Values.copy(), vox.Colors.copy(), mesh.Vertices.copy(), mesh.Colors.copy(), mesh.Normals.copy(), np.asarray(mesh.Triangles).copy(),
+                    img.Array.copy(), sdf(pts)))
+    for a, b in zip(*res):
+        if a.dtype == np.float32:
+            assert_bits_equal(a, b, name)
+        else:
+            assert np.array_equal(a, b)
+    ref = oracle.eval_sdf(sdf.lowered, pts[:5])
+    assert_bits_equal(res[0][7][:5], ref, name + " special points vs oracle")
+
+
 def test_packed_sqrt_is_exhaustively_exact(sk):
     """sk2_sqrt (csrc/sdfk_prelude.h) against sqrt.rn.f32 for ALL 2^32 arguments (and scrambled partners in the other half)."""
     from sdfkit_b200 import _native as N

@@ -209,7 +209,7 @@ def test_packed_body_compiles_offline_and_never_adds_packed_products(name):
     from sdfkit_b200 import _native as N, scenes
     from sdfkit_b200.exprs import PACKED_MARKER, lower
     expr = {"sphere": scenes.sphere, "readme": scenes.readme_scene, "perf": scenes.perf_scene, "csg50": scenes.csg50}[name]()[0]
-    low = lower(expr, fast_div=lambda c: True)
+    low = lower(expr, fast_div=lambda c: True, packed=True)
     assert "sk2_" not in low.body and low.body == lower(expr).body
     products = set(re.findall(r"const sk_f2 (v\d+) = sk2_mul\(", low.body2))
     for line in low.body2.splitlines():
@@ -220,6 +220,41 @@ def test_packed_body_compiles_offline_and_never_adds_packed_products(name):
     n = C.c_size_t()
     N.check(N.lib().sdfk_sdf_check(text, len(text), C.byref(n)))
     assert n.value > 10000
+
+
+@pytest.mark.parametrize("name", ["sphere", "readme", "perf", "csg50"])
+def test_shared_guard_device_forms(name):
+    """The default device forms (two-point evaluator, row-of-voxels evaluator): NVRTC accepts them for sm_100a without a GPU;
+    the scalar body the oracle compiles is untouched by them; in the grid form only z-dependent operations get a shared guard
+    (x/y-only ones stay plain instructions the compiler hoists out of the z loop); every verified constant division and every
+    sqrt appears exactly as often as in the scalar body times the number of points."""
+    import ctypes as C
+    import re
+    from sdfkit_b200 import _native as N, scenes
+    from sdfkit_b200.exprs import GRID_M, GRID_MARKER, PACKED_MARKER, lower
+    expr = {"sphere": scenes.sphere, "readme": scenes.readme_scene, "perf": scenes.perf_scene, "csg50": scenes.csg50}[name]()[0]
+    low = lower(expr, fast_div=lambda c: True)
+    assert low.body == lower(expr).body and "sk_sqrt_core" not in low.body and "sk_divc_core" not in low.body
+    nsqrt, ndiv = low.op_counts.get("sqrt", 0), low.op_counts.get("div", 0)
+    count = lambda text, pat: len(re.findall(pat, text))
+    # pair form: every sqrt of both points is either in a group (core + IEEE redo) or plain
+    st = low.guard_stats["pair"]
+    assert st["sqrt_grouped"] + st["sqrt_plain"] == 2 * nsqrt and st["div_grouped"] + st["div_plain"] <= 2 * ndiv
+    assert count(low.pair_body, r"sk_sqrt_core\(") == st["sqrt_grouped"]
+    assert count(low.pair_body, r"sk_divc_core\(") == st["div_grouped"]
+    # grid form: y/z-only work is emitted once, x-dependent work GRID_M times
+    sg = low.guard_stats["grid"]
+    assert "#define SDFK_GRID_M %d" % GRID_M in low.grid_text
+    assert sg["sqrt_grouped"] + sg["sqrt_plain"] <= GRID_M * nsqrt
+    if name == "readme":
+        assert sg == {"sqrt_groups": 1, "sqrt_grouped": 4, "div_groups": 0, "div_grouped": 0, "sqrt_plain": 0, "div_plain": 0}
+        assert count(low.grid_text, r" / ") == 2 * GRID_M + 2          # x divisions per voxel, y divisions once: all plain (hoistable)
+    text = (low.body + PACKED_MARKER + "\n" + low.pair_body + GRID_MARKER + "\n" + low.grid_text).encode()
+    n = C.c_size_t()
+    N.check(N.lib().sdfk_sdf_check(text, len(text), C.byref(n)))
+    assert n.value > 10000
+    # a host that sends only the scalar body (the C# shim) gets the library's default device forms
+    N.check(N.lib().sdfk_sdf_check(low.body.encode(), len(low.body), C.byref(n)))
 
 
 def test_cost_balanced_plan_weights():
