@@ -40,7 +40,7 @@ class GpuSdf:
         # (README ToImage 0.189 -> 0.236 ms, CSG-50 sampling 10.8 -> 16.5 ms: register pairs, per-half traffic), so it is off
         # by default; DESIGN.md section 2b.
         import os
-        from .exprs import GRID_MARKER, PACKED_MARKER
+        from .exprs import PACKED_MARKER
         packed = os.environ.get("SDFK_PACKED", "0") == "1"
         plain = os.environ.get("SDFK_PLAIN_BODY", "0") == "1"        # debugging: only the scalar body, the library's default device forms
         # Division by a constant may use the 3-instruction correctly rounded sequence once the device has compared it with
@@ -54,7 +54,7 @@ class GpuSdf:
         else:
             # the scalar body (what the oracle compiles) + the device forms: two-point evaluator and row-of-voxels evaluator with
             # shared range guards (exprs._emit_multi) -- same IEEE operations, bit-identical results
-            text = low.body + PACKED_MARKER + "\n" + low.pair_body + GRID_MARKER + "\n" + low.grid_text
+            text = low.device_text()
         body = text.encode()
         h = C.c_void_p()
         N.check(N.lib().sdfk_sdf_compile(self.ctx.handle, body, len(body), C.byref(h)))

@@ -556,6 +556,23 @@ def test_default_device_forms_equal_plain_scalar_body(sk, oracle, monkeypatch, n
     assert_bits_equal(res[0][7][:5], ref, name + " special points vs oracle")
 
 
+def test_color_table_rewrite_is_bit_identical(sk, oracle, monkeypatch):
+    """Opt-in colour-table form of a union of constant-coloured primitives (exprs._color_table_rewrite): same voxels and image."""
+    import importlib
+    from sdfkit_b200 import exprs, scenes
+    expr, mn, mx = scenes.csg50()
+    monkeypatch.setattr(exprs, "_CTAB", True)
+    sdf = expr.ToSdf()
+    assert "sdfk_ctab" in sdf.lowered.decls
+    vox = sdf.ToVoxels(mn, mx, 96, 96, 48)
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), 96, 96, 48, clip_to_bounds=True, threads=4)
+    assert_bits_equal(vox.Values, ov, "distances")
+    assert_bits_equal(vox.Colors, oc, "colours")
+    img = sdf.ToImage(64, 48, *scenes.CAMERA)
+    from sdfkit_b200 import numerics
+    assert_bits_equal(img.Array, oracle.render(sdf.lowered, 64, 48, view=numerics.create_look_at(*scenes.CAMERA), bands=2), "image")
+
+
 def test_packed_sqrt_is_exhaustively_exact(sk):
     """sk2_sqrt (csrc/sdfk_prelude.h) against sqrt.rn.f32 for ALL 2^32 arguments (and scrambled partners in the other half)."""
     from sdfkit_b200 import _native as N

@@ -249,10 +249,23 @@ def test_shared_guard_device_forms(name):
     if name == "readme":
         assert sg == {"sqrt_groups": 1, "sqrt_grouped": 4, "div_groups": 0, "div_grouped": 0, "sqrt_plain": 0, "div_plain": 0}
         assert count(low.grid_text, r" / ") == 2 * GRID_M + 2          # x divisions per voxel, y divisions once: all plain (hoistable)
-    text = (low.body + PACKED_MARKER + "\n" + low.pair_body + GRID_MARKER + "\n" + low.grid_text).encode()
+    text = low.device_text().encode()
     n = C.c_size_t()
     N.check(N.lib().sdfk_sdf_check(text, len(text), C.byref(n)))
     assert n.value > 10000
+    assert low.decls == "" and "ctab" not in text.decode()
+    low = lower(expr, fast_div=lambda c: True, color_table=True)       # opt-in rewrite (measured slower: off by default)
+    text = low.device_text().encode()
+    N.check(N.lib().sdfk_sdf_check(text, len(text), C.byref(n)))
+    if name == "csg50":
+        # the union of coloured primitives: the colour decision tree became a table (12 primitives + the subtracted sphere) and an
+        # integer carried through the same comparisons; no colour select is left in the device forms
+        assert low.decls.count("{") == 1 + 13 and "sdfk_ctab[13]" in low.decls
+        assert low.pair_body.count("const int i") == 2 * 12 and low.grid_text.count("const int i") == GRID_M * 12
+        assert low.pair_body.count("sk_sel(") == 2 * 12          # the distance selects remain: one per union / subtract
+        assert low.body.count("sk_sel(") == 4 * 12 and "ctab" not in low.body
+    else:
+        assert low.decls == ""
     # a host that sends only the scalar body (the C# shim) gets the library's default device forms
     N.check(N.lib().sdfk_sdf_check(low.body.encode(), len(low.body), C.byref(n)))
 
