@@ -548,12 +548,14 @@ static int multi_to_mesh_host(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
     std::vector<std::array<double, 4>> stage_ms((size_t)n, std::array<double, 4>{{0, 0, 0, 0}});
     std::atomic<int> failed{0};
     Team* team = c->team;
+    if (g_trace) fprintf(stderr, "[sdfk] multi to_mesh_host: plan %.3f ms\n", wall.ms());
     int rc = team->run([&](int r) -> int {
         sdfk_ctx* d = c->devs[(size_t)r];
         const int kb = layers[(size_t)r].first, ke = layers[(size_t)r].second;
         sdfk_voxels* v = nullptr;
         sdfk_mesh* m = nullptr;
         int rr = SDFK_OK;
+        WallClock wr;
         if (ke > kb) {
             Lock l(d);
             if (!d->copy_stream && cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -568,7 +570,9 @@ static int multi_to_mesh_host(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
             if (rr == SDFK_OK) { nv[(size_t)r] = m->nverts; nt[(size_t)r] = m->ntris; }
         }
         if (rr) failed.store(1);
+        const double t_classified = wr.ms();
         team->barrier();                                    // counts of every slab are in host memory
+        const double t_barrier = wr.ms();
         if (!failed.load() && r == 0) {                     // device 0's thread sizes the ONE host result (recycled page-locked buffers)
             Lock l(c);
             int64_t vt = 0, tt = 0;
@@ -605,6 +609,8 @@ static int multi_to_mesh_host(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
                 if (e != cudaSuccess) rr = fail(SDFK_ERR_CUDA, "sdfk_sdf_to_mesh_host: %s", cudaGetErrorString(e));
             }
             if (rr == SDFK_OK && m->hs->err) rr = fail(SDFK_ERR_INTERNAL, "marching-cubes emit: inconsistent vertex ownership (code %d)", m->hs->err);
+            if (g_trace) fprintf(stderr, "[sdfk] dev %d layers [%d,%d): classified %.3f barrier %.3f done %.3f ms, %lld vertices\n", r, kb, ke,
+                                 t_classified, t_barrier, wr.ms(), (long long)m->nverts);
             if (rr == SDFK_OK) {
                 mesh_stage_times(m);
                 if (m->nverts > 0) { decode_aabb(m->hs->keys, boxes[(size_t)r].data()); has_box[(size_t)r] = 1; }

@@ -1,0 +1,37 @@
+#!/usr/bin/env python3
+"""Multi-GPU context timing: Sdf.ToMesh (one host mesh) and the device-resident step on 1..N devices.
+usage: python tools/time_multi.py [n] [ndev ...]   (SDFK_TRACE=1 prints the per-device phases)"""
+import os
+import sys
+import time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import sdfkit_b200 as sk
+from bench import scene_by_name
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+devs = [int(a) for a in sys.argv[2:]] or [d for d in (1, 2, 4, 8) if d <= torch.cuda.device_count()]
+expr, mn, mx = scene_by_name(os.environ.get("SCENE", "readme"))
+for nd in devs:
+    ctx = sk.Context(devices=list(range(nd)))
+    sdf = sk.GpuSdf(expr, ctx=ctx)
+    ts = []
+    for it in range(8):
+        t0 = time.perf_counter()
+        m = sdf.ToMesh(mn, mx, n, n, n)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    vox = sdf.ToVoxels(mn, mx, n, n, n)
+    td = []
+    for it in range(8):
+        t0 = time.perf_counter()
+        vox.Resample(sdf, clip=True)
+        gm = sk.MarchingCubes.CreateGpuMesh(vox)
+        td.append((time.perf_counter() - t0) * 1e3)
+        gm.destroy()
+    print("%d devices  %d^3: ToMesh(host) best %.3f median %.3f ms | device step best %.3f median %.3f ms | %d tris" % (
+        nd, n, min(ts[2:]), sorted(ts[2:])[3], min(td[2:]), sorted(td[2:])[3], len(m.Triangles) // 3), flush=True)
+    del m
+    vox.Dispose()
+    sdf.Dispose()
+    ctx.close()
