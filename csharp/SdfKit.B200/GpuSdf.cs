@@ -13,6 +13,8 @@ namespace SdfKit.B200
     {
         public GpuContext Context { get; }
         public string Body { get; }
+        /// <summary>The tree this SDF was compiled from (WithColor re-compiles a modified tree).</summary>
+        public System.Linq.Expressions.Expression<SdfFunc>? Expression { get; private set; }
 
         GpuSdf(GpuContext ctx, string body) : base(IntPtr.Zero, true)
         {
@@ -30,9 +32,16 @@ namespace SdfKit.B200
         /// <summary>Replacement body of SdfExprCompiler.Compile (SdfKit/SdfExpr.cs:234-238).</summary>
         public static Sdf Compile(System.Linq.Expressions.Expression<SdfFunc> expression, GpuContext? ctx = null)
         {
-            var gpu = new GpuSdf(ctx ?? GpuContext.Shared, SdfExprLowering.Lower(expression));
+            var gpu = new GpuSdf(ctx ?? GpuContext.Shared, SdfExprLowering.Lower(expression)) { Expression = expression };
             return gpu.Invoke;   // delegate.Target == gpu
         }
+
+        /// <summary>SdfEx.WithColor (SdfKit/Sdf.cs:101-115) for a compiled SDF.  The reference wraps the delegate in an opaque
+        /// lambda that overwrites the colour of every output; the same values come from the tree with a constant colour
+        /// (SdfExprEx.Color, SdfKit/SdfExpr.cs:143-147), which stays on the GPU path -- the Python mirror does the same
+        /// (sdfkit_b200/sdf.py: WithColor; tests/test_gpu_multi.py::test_with_color_matches_oracle).</summary>
+        public Sdf WithColor(Vector3 color) =>
+            Compile((Expression ?? throw new NotSupportedException("this GpuSdf was not built from an SdfExpr")).Color(color), Context);
 
         /// <summary>The delegate body: colorsAndDistances[i] = sdf(points[i]) (SdfKit/Sdf.cs:8).</summary>
         public void Invoke(Memory<Vector3> points, Memory<Vector4> colorsAndDistances)

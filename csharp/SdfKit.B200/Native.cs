@@ -16,6 +16,9 @@ namespace SdfKit.B200
         [DllImport(Lib)] public static extern int sdfk_version();
 
         [DllImport(Lib)] public static extern int sdfk_ctx_create(int device, out IntPtr ctx);
+        // N GPUs of one box behind one handle: sampling / meshing shard by z-slab, rendering by row band, inside the library
+        [DllImport(Lib)] public static extern int sdfk_ctx_create_multi(int ndev, int[]? devices, out IntPtr ctx);
+        [DllImport(Lib)] public static extern int sdfk_ctx_device_count(IntPtr ctx, out int ndev);
         [DllImport(Lib)] public static extern int sdfk_ctx_destroy(IntPtr ctx);
         [DllImport(Lib)] public static extern int sdfk_ctx_synchronize(IntPtr ctx);
 
@@ -44,11 +47,16 @@ namespace SdfKit.B200
         [DllImport(Lib)] public static extern int sdfk_ctx_set_option(IntPtr ctx, int option, int value);
         [DllImport(Lib)] public static extern int sdfk_mesh_destroy(IntPtr mesh);
 
-        // Not bound here (not needed by the single-process drop-in; see include/sdfk.h): instrumentation (sdfk_ctx_mark / _elapsed /
-        // _timer_* / _launch_count / _stream / _create_on_stream, sdfk_mesh_stats, sdfk_sdf_check), the multi-GPU slab API
-        // (sdfk_voxels_sample_slab / _sample_distances / _resample / _info, sdfk_mesh_classify / _emit / _emit_host /
-        // _device_ptrs, sdfk_render_device), pinned-buffer helpers (sdfk_host_alloc / _free), the packed-evaluator self-tests
-        // (sdfk_constdiv_verify, sdfk_selftest_sqrt) and sdfk_render_bgr8 (TGA payload packed on the device).
+        // Not bound here (not needed by the drop-in; see include/sdfk.h): instrumentation (sdfk_ctx_mark / _elapsed / _timer_* /
+        // _launch_count / _last_wall_ms / _stream / _create_on_stream, sdfk_mesh_stats, sdfk_sdf_check), the per-process slab API of
+        // the torchrun path (sdfk_voxels_sample_slab / _sample_distances / _resample / _info / _layers / _part, sdfk_mesh_classify /
+        // _emit / _emit_host / _device_ptrs / _part, sdfk_plan_layers, sdfk_render_device), pinned-buffer helpers (sdfk_host_alloc /
+        // _free) and the exhaustive self-tests (sdfk_constdiv_verify, sdfk_selftest_sqrt).
+        // Vec3Data.SaveTga / FloatData.SaveDepthTga payloads packed on the device (a quarter of the float image over PCIe):
+        [DllImport(Lib)] public static extern int sdfk_render_bgr8(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos, float* invViewProj,
+            float near, float far, int iterations, int rowBegin, int rowEnd, byte* bgr);
+        [DllImport(Lib)] public static extern int sdfk_render_depth_gray8(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos,
+            float* invViewProj, float marchNear, int iterations, float tgaNear, float tgaFar, int rowBegin, int rowEnd, byte* gray);
         [DllImport(Lib)] public static extern int sdfk_render(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos, float* invViewProj,
             float near, float far, int iterations, int rowBegin, int rowEnd, float* rgb);
         [DllImport(Lib)] public static extern int sdfk_render_depth(IntPtr ctx, IntPtr sdf, int w, int h, float* camPos,
@@ -63,11 +71,17 @@ namespace SdfKit.B200
         }
     }
 
-    /// <summary>One GPU + one stream; shared by every GpuSdf of the process.</summary>
+    /// <summary>The GPU(s) behind every GpuSdf of the process: one device, or -- SDFK_DEVICES=0,1,2,3 / new GpuContext(new[]{..}) --
+    /// several devices of one box behind one handle (sdfk_ctx_create_multi).  ToVoxels / ToMesh / ToImage then shard inside the
+    /// library (z-slabs, row bands) and land ONE result; nothing else in the managed code changes.</summary>
     public sealed class GpuContext : SafeHandle
     {
-        static readonly Lazy<GpuContext> shared = new(() => new GpuContext(
-            int.TryParse(Environment.GetEnvironmentVariable("LOCAL_RANK"), out var r) ? r : 0));
+        static readonly Lazy<GpuContext> shared = new(() => {
+            var list = Environment.GetEnvironmentVariable("SDFK_DEVICES");
+            if (!string.IsNullOrWhiteSpace(list))
+                return new GpuContext(Array.ConvertAll(list.Split(','), x => int.Parse(x.Trim())));
+            return new GpuContext(int.TryParse(Environment.GetEnvironmentVariable("LOCAL_RANK"), out var r) ? r : 0);
+        });
         public static GpuContext Shared => shared.Value;
 
         public GpuContext(int device) : base(IntPtr.Zero, true)
@@ -75,6 +89,14 @@ namespace SdfKit.B200
             Native.Check(Native.sdfk_ctx_create(device, out var h));
             SetHandle(h);
         }
+
+        public GpuContext(int[] devices) : base(IntPtr.Zero, true)
+        {
+            Native.Check(Native.sdfk_ctx_create_multi(devices.Length, devices, out var h));
+            SetHandle(h);
+        }
+
+        public int DeviceCount { get { Native.Check(Native.sdfk_ctx_device_count(handle, out var n)); return n; } }
         public override bool IsInvalid => handle == IntPtr.Zero;
         protected override bool ReleaseHandle() => Native.sdfk_ctx_destroy(handle) == 0;
         internal IntPtr Ptr => handle;

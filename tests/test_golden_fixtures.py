@@ -97,3 +97,19 @@ def test_gpu_images_match_fixtures(name):
     expr, _, _ = G.scene(rec["scene"])
     img = expr.ToSdf().ToImage(rec["w"], rec["h"], *scenes.CAMERA)
     assert digest(img.Array, np.float32) == rec["sha256_rgb"], name
+
+
+def test_dialect_text_of_the_benchmark_scenes_is_pinned():
+    """tests/golden/dialect_bodies.json: the scalar dialect body of the four BASELINE scenes.  The C# SdfExprLowering
+    (csharp/SdfKit.B200, never compiled here) has to emit the same operations in the same order for the same trees; this test
+    holds the Python lowering to the committed text, so a change of the dialect is a visible diff of the fixture."""
+    import json
+    import os
+    from sdfkit_b200 import scenes
+    from sdfkit_b200.exprs import lower
+    fix = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dialect_bodies.json")))
+    for name, fn in (("sphere", scenes.sphere), ("readme", scenes.readme_scene), ("perf", scenes.perf_scene), ("csg50", scenes.csg50)):
+        low = lower(fn()[0])
+        assert low.body == fix[name]["body"], name
+        assert low.flops == fix[name]["flops"] and low.node_count == fix[name]["node_count"]
+    assert fix["readme"]["flops"] == 23 and fix["csg50"]["flops"] == 205 and fix["csg50"]["node_count"] == 50
