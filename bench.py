@@ -379,7 +379,7 @@ def pcie_aggregate(ndevs):
     return out
 
 
-def strong_record(sk, expr, mn, mx, n, ndevs, steps, single_mesh_sha, scene):
+def strong_record(sk, expr, mn, mx, n, ndevs, steps, single_mesh_sha, scene, config4=True):
     """The same n^3 job on 1, 2, 4, .. devices behind sdfk_ctx_create_multi: (a) device-resident step = sharded Voxels
     (16 B/voxel) + MarchingCubes, (b) e2e = Sdf.ToMesh landing ONE host mesh.  Wall clock from call to completion on all
     devices (+ the slowest device's own event span); every result is compared with the single-GPU digest."""
@@ -388,6 +388,7 @@ def strong_record(sk, expr, mn, mx, n, ndevs, steps, single_mesh_sha, scene):
                    "the cost-balanced planner, counts exchanged in host memory, every device copies its share of the mesh to its offset of "
                    "one host result over its own PCIe link"}
     gold = golden_digest(scene, n)
+    render_sha = [None]
     for nd in ndevs:
         ctx = sk.Context(devices=list(range(nd)))
         try:
@@ -429,6 +430,37 @@ def strong_record(sk, expr, mn, mx, n, ndevs, steps, single_mesh_sha, scene):
                    "d2h_bytes_per_step": d2h, "vertices": nv, "triangles": nt,
                    "equal_to_single_gpu": {"device_resident": sha_res == single_mesh_sha, "e2e": sha_e2e == single_mesh_sha},
                    "equal_to_golden_digest": None if gold is None else (sha_e2e == gold["sha256"])}
+            # BASELINE config 5 on nd devices: the image in row bands (RayMarcher.cs:50-61), one per device, one host image
+            from sdfkit_b200 import scenes as _sc
+            imgs = []
+            for it in range(6):
+                t0 = time.perf_counter()
+                img = sdf.ToImage(1920, 1080, *_sc.CAMERA, depthIterations=40)
+                imgs.append((time.perf_counter() - t0) * 1e3)
+            isha = hashlib.sha256(img.Array.tobytes()).hexdigest()
+            if render_sha[0] is None:
+                render_sha[0] = isha
+            rec["toimage_1080p_ms"] = statistics.median(imgs[2:])
+            rec["toimage_equal_to_single_gpu"] = isha == render_sha[0]
+            del img
+            # BASELINE config 4: the same scene at 2048^3 (137 GB of voxels if materialised) through Sdf.ToMesh on nd >= 2 devices
+            if nd >= 2 and config4:
+                try:
+                    g4 = golden_digest(scene, 2048)
+                    t4 = []
+                    for it in range(4):
+                        t0 = time.perf_counter()
+                        m4 = sdf.ToMesh(mn, mx, 2048, 2048, 2048)
+                        t4.append((time.perf_counter() - t0) * 1e3)
+                        if it < 3:
+                            del m4
+                    rec["config4_2048"] = {"e2e_ms": statistics.median(t4[1:]), "e2e_voxels_per_s": 2048 ** 3 / (statistics.median(t4[1:]) * 1e-3),
+                                           "vertices": int(len(m4.Vertices)), "triangles": int(len(m4.Triangles) // 3),
+                                           "d2h_bytes_per_step": m4.Vertices.nbytes * 3 + m4.Triangles.nbytes,
+                                           "equal_to_golden_digest": None if g4 is None else (mesh_sha(m4) == g4["sha256"])}
+                    del m4
+                except Exception as ex:
+                    rec["config4_2048"] = {"error": repr(ex)[:300]}
             out["by_devices"][str(nd)] = rec
             sdf.Dispose()
         finally:

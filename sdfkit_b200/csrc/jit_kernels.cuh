@@ -35,6 +35,13 @@ struct sdfk_sample_params {
     float sign_iso;            // iso value of the sign planes (see below)
 };
 
+// the work decomposition of sdfk_k_sample_dist8, whose warps own PAIRS of tiles (256 x of one y).  (A separate kernel
+// parameter: appended to sdfk_sample_params it changed the code generated for the other two sampling kernels, +13 % on K1d.)
+struct sdfk_sample8_params {
+    unsigned ncol8, zsplit8, nwork8;
+    sdfk_fastdiv div_tpr8, div_ncol8;
+};
+
 #define SDFK_SAMPLE_WARPS 8
 
 // Sign blocks: a by-product of sampling that lets marching cubes find the active cells without re-reading the
@@ -259,6 +266,89 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
         }
     }
 }
+
+
+// K1d with 8 voxels per lane: a warp owns a PAIR of neighbouring tiles (256 consecutive x of one y).  The distance-only
+// sampler is bound by instruction issue, not by HBM, and a third of its instructions per slice do not depend on how many
+// voxels the lane evaluates (slice position, loop control, addresses, constant loads): twice the voxels per slice halve
+// that share.  Used when every row is a whole number of tile pairs (nx % 256 == 0); same sign blocks, same values.
+// Only for small SDF bodies (the lowering defines SDFK_DIST8): measured at 1024^3, README scene 0.765 -> 0.726 ms, but the
+// Perf scene 1.60 -> 1.74 ms and CSG-50 7.6 -> 14.2 ms -- twice the hoisted per-voxel state no longer fits the registers.
+#ifdef SDFK_DIST8
+extern "C" __global__ void __launch_bounds__(SDFK_SAMPLE_WARPS * 32)
+sdfk_k_sample_dist8(const sdfk_sample_params P, const sdfk_sample8_params Q, float* __restrict__ dist, uint4* __restrict__ signs)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    const size_t plane = (size_t)P.nx * (size_t)P.ny;
+    const size_t colwords = (size_t)((P.nzl + 31) >> 5) * 32u;
+
+    for (unsigned work = blockIdx.x * SDFK_SAMPLE_WARPS + warp; work < Q.nwork8; work += gridDim.x * SDFK_SAMPLE_WARPS) {
+        const unsigned seg = sdfk_div(work, Q.div_ncol8);
+        const unsigned col = work - seg * Q.ncol8;
+        const unsigned uy = sdfk_div(col, Q.div_tpr8);
+        const unsigned xp = col - uy * (P.tiles_per_row >> 1);          // tile pair of the row: tiles 2 xp, 2 xp + 1
+        const int iy = (int)uy;
+        int zl0, zl1;
+        {
+            const long long a = ((long long)seg * P.nzl) / Q.zsplit8, b = ((long long)(seg + 1) * P.nzl) / Q.zsplit8;
+            zl0 = seg == 0u ? 0 : min(P.nzl, (int)((a + 31) & ~31ll));
+            zl1 = seg + 1u == Q.zsplit8 ? P.nzl : min(P.nzl, (int)((b + 31) & ~31ll));
+        }
+        const int x0 = (int)(xp * 256u + lane * 4u);                   // first voxel of the lane in tile A; tile B: + 128
+        const float py = P.m1 + (float)iy * P.dy;
+        const bool rowwall = P.clip && (iy == 0 || iy == P.ny - 1);
+        float px[8];
+        unsigned keep[8], setb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int x = x0 + (k & 3) + ((k >> 2) << 7);
+            px[k] = P.m0 + (float)x * P.dx;
+            const bool w = P.clip && (x == 0 || x == P.nx - 1);
+            keep[k] = w ? 0u : 0xFFFFFFFFu;
+            setb[k] = w ? __float_as_uint(P.clip_value) : 0u;
+        }
+        size_t vbase = ((size_t)zl0 * P.ny + uy) * (size_t)P.nx + (size_t)(xp * 256u);
+        uint4* const scol = signs + ((size_t)uy * P.tiles_per_row + 2u * xp) * colwords + lane;     // tile A; tile B: + colwords
+
+        for (int zg0 = zl0; zg0 < zl1; zg0 += 32) {
+            uint4 swa = make_uint4(0u, 0u, 0u, 0u), swb = make_uint4(0u, 0u, 0u, 0u);
+            for (int zb0 = zg0; zb0 < min(zg0 + 32, zl1); zb0 += 8) {
+                const int zend = min(zb0 + 8, zl1);
+                const bool walls = rowwall || (P.clip && (zb0 + P.z_begin == 0 || zend + P.z_begin == P.nz));
+                unsigned sa = 0u, sb = 0u, ssh = 0u;
+                for (int zl = zb0; zl < zend; zl++, vbase += plane, ssh += 4u) {
+                    const int iz = zl + P.z_begin;
+                    float d[8];
+                    if (walls && (rowwall || (P.clip && (iz == 0 || iz == P.nz - 1)))) {      // warp-uniform
+#pragma unroll
+                        for (int k = 0; k < 8; k++) d[k] = P.clip_value;
+                    } else {
+                        const float pz = P.m2 + (float)iz * P.dz;
+                        sk_float4 r8[8];
+                        sdf_eval_grid(px, py, pz, r8);
+                        sdf_eval_grid(px + 4, py, pz, r8 + 4);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) d[k] = __uint_as_float((__float_as_uint(r8[k].w) & keep[k]) | setb[k]);
+                    }
+                    sa |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
+                    sb |= sdfk_sign_nibble(d + 4, P.sign_iso) << ssh;
+                    float4* const out = reinterpret_cast<float4*>(dist + vbase) + lane;
+                    __stcs(out, make_float4(d[0], d[1], d[2], d[3]));
+                    __stcs(out + 32, make_float4(d[4], d[5], d[6], d[7]));
+                }
+                const int sq = (zb0 >> 3) & 3;
+                if (sq == 0) { swa.x = sa; swb.x = sb; } else if (sq == 1) { swa.y = sa; swb.y = sb; }
+                else if (sq == 2) { swa.z = sa; swb.z = sb; } else { swa.w = sa; swb.w = sb; }
+            }
+            if (signs) {
+                __stcs(scol + (size_t)(zg0 >> 5) * 32u, swa);
+                __stcs(scol + colwords + (size_t)(zg0 >> 5) * 32u, swb);
+            }
+        }
+    }
+}
+#endif
 
 // Deferred vertex colours for distance-only voxels.  recipes[t] = (cell, edge) that created vertex t; the colour is
 // recomputed exactly as Cell.AddFaceFromEdgeIndex / CalculateCenterVertex do (Cell.cs:313-357,501-549): corner colours

@@ -549,25 +549,35 @@ static int multi_to_mesh_host(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
     std::atomic<int> failed{0};
     Team* team = c->team;
     if (g_trace) fprintf(stderr, "[sdfk] multi to_mesh_host: plan %.3f ms\n", wall.ms());
+    // A device's layer range is meshed in sub-slabs of at most `cap` cell layers: 32-bit cell ids bound one meshing job to
+    // 2^32 cells (2048^2 cells per layer: 1023 layers), and 256-layer blocks keep the allocations recyclable.
+    const long long cells_per_layer = (long long)std::max(1, cells_along(nx, step)) * std::max(1, cells_along(ny, step));
+    int cap = (int)std::max<long long>(1, std::min<long long>(256, 0xFFFFFFF0ll / cells_per_layer - 2));
+    if (const char* env = getenv("SDFK_SUBSLAB_CAP")) cap = std::max(1, atoi(env));     // (tests: force several sub-slabs on small grids)
+    struct Sub { sdfk_voxels* v = nullptr; sdfk_mesh* m = nullptr; int kb = 0, ke = 0; };
     int rc = team->run([&](int r) -> int {
         sdfk_ctx* d = c->devs[(size_t)r];
         const int kb = layers[(size_t)r].first, ke = layers[(size_t)r].second;
-        sdfk_voxels* v = nullptr;
-        sdfk_mesh* m = nullptr;
+        std::vector<Sub> subs;
+        for (int a = kb; a < ke; a += cap) { Sub sb; sb.kb = a; sb.ke = std::min(ke, a + cap); subs.push_back(sb); }
         int rr = SDFK_OK;
         WallClock wr;
         if (ke > kb) {
             Lock l(d);
             if (!d->copy_stream && cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
                 rr = fail(SDFK_ERR_CUDA, "cudaStreamCreate failed");
-            int z0, z1;
-            slab_slices(kb, ke, step, nz, z0, z1);
-            if (rr == SDFK_OK) rr = voxels_alloc(d, mn, mx, nx, ny, nz, z0, z1, &v, false);
-            if (rr == SDFK_OK) rr = voxels_sample_into(v, s->parts[(size_t)r], clip, iso);
-            if (rr == SDFK_OK) rr = mesh_stage_a(d, v, iso, step, kb, ke, &m);
-            if (rr == SDFK_OK) rr = mesh_stage_b(m);
-            if (rr == SDFK_OK) rr = mesh_stage_b_finish(m);
-            if (rr == SDFK_OK) { nv[(size_t)r] = m->nverts; nt[(size_t)r] = m->ntris; }
+            for (auto& sb : subs) {                              // stage A of every sub-slab, enqueued back to back
+                int z0, z1;
+                slab_slices(sb.kb, sb.ke, step, nz, z0, z1);
+                if (rr == SDFK_OK) rr = voxels_alloc(d, mn, mx, nx, ny, nz, z0, z1, &sb.v, false);
+                if (rr == SDFK_OK) rr = voxels_sample_into(sb.v, s->parts[(size_t)r], clip, iso);
+                if (rr == SDFK_OK) rr = mesh_stage_a(d, sb.v, iso, step, sb.kb, sb.ke, &sb.m);
+            }
+            for (auto& sb : subs) {
+                if (rr == SDFK_OK) rr = mesh_stage_b(sb.m);
+                if (rr == SDFK_OK) rr = mesh_stage_b_finish(sb.m);
+                if (rr == SDFK_OK) { nv[(size_t)r] += sb.m->nverts; nt[(size_t)r] += sb.m->ntris; }
+            }
         }
         if (rr) failed.store(1);
         const double t_classified = wr.ms();
@@ -586,43 +596,54 @@ static int multi_to_mesh_host(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], const
             R->ntris = tt;
         }
         team->barrier();
-        if (failed.load()) {
-            if (m) { Lock l(d); m->vox = nullptr; mesh_free_device(m); delete m; }
-            if (v) { Lock l(d); voxels_free(v); }
-            return rr;
-        }
-        if (m) {
+        if (!failed.load() && ke > kb) {
             Lock l(d);
             int64_t vb = 0, tb = 0;
             for (int q = 0; q < r; q++) { vb += nv[(size_t)q]; tb += nt[(size_t)q]; }
-            EmitPlan plan;
-            plan.host = R->host;
-            plan.copy = d->copy_stream;
-            plan.host_voff = (size_t)vb * 12;
-            plan.host_toff = (size_t)tb * 12;
-            cudaError_t e = build_emit_plan(m, 0, plan);
-            if (e != cudaSuccess) rr = fail(SDFK_ERR_CUDA, "emit plan: %s", cudaGetErrorString(e));
-            if (rr == SDFK_OK) rr = mesh_emit_async(m, vb, tb, M, N, nullptr, nullptr, &plan);
-            if (rr == SDFK_OK) {
-                e = cudaStreamSynchronize(m->ws ? m->ws : d->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(d->copy_stream);
-                if (e != cudaSuccess) rr = fail(SDFK_ERR_CUDA, "sdfk_sdf_to_mesh_host: %s", cudaGetErrorString(e));
+            for (auto& sb : subs) {                              // emit in sub-ranges, every finished part on its way to the host
+                sdfk_mesh* m = sb.m;
+                EmitPlan plan;
+                plan.host = R->host;
+                plan.copy = d->copy_stream;
+                plan.host_voff = (size_t)vb * 12;
+                plan.host_toff = (size_t)tb * 12;
+                cudaError_t e = build_emit_plan(m, 0, plan);
+                if (e != cudaSuccess && rr == SDFK_OK) rr = fail(SDFK_ERR_CUDA, "emit plan: %s", cudaGetErrorString(e));
+                if (rr == SDFK_OK) rr = mesh_emit_async(m, vb, tb, M, N, nullptr, nullptr, &plan);
+                vb += m->nverts;
+                tb += m->ntris;
             }
-            if (rr == SDFK_OK && m->hs->err) rr = fail(SDFK_ERR_INTERNAL, "marching-cubes emit: inconsistent vertex ownership (code %d)", m->hs->err);
-            if (g_trace) fprintf(stderr, "[sdfk] dev %d layers [%d,%d): classified %.3f barrier %.3f done %.3f ms, %lld vertices\n", r, kb, ke,
-                                 t_classified, t_barrier, wr.ms(), (long long)m->nverts);
-            if (rr == SDFK_OK) {
+            cudaError_t e = cudaStreamSynchronize(d->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(d->copy_stream);
+            if (e != cudaSuccess && rr == SDFK_OK) rr = fail(SDFK_ERR_CUDA, "sdfk_sdf_to_mesh_host: %s", cudaGetErrorString(e));
+            for (auto& sb : subs) {
+                sdfk_mesh* m = sb.m;
+                if (rr == SDFK_OK && m->hs->err) rr = fail(SDFK_ERR_INTERNAL, "marching-cubes emit: inconsistent vertex ownership (code %d)", m->hs->err);
+                if (rr != SDFK_OK) break;
                 mesh_stage_times(m);
-                if (m->nverts > 0) { decode_aabb(m->hs->keys, boxes[(size_t)r].data()); has_box[(size_t)r] = 1; }
-                nact[(size_t)r] = (int64_t)m->rec_end - (int64_t)m->rec_begin;
-                nchunks[(size_t)r] = m->g.nchunks;
-                from_signs[(size_t)r] = m->from_signs ? 1 : 0;
-                for (int k = 0; k < 4; k++) stage_ms[(size_t)r][(size_t)k] = m->ms[k];
+                if (m->nverts > 0) {
+                    float bx[6];
+                    decode_aabb(m->hs->keys, bx);
+                    for (int k = 0; k < 3; k++) {
+                        boxes[(size_t)r][(size_t)k] = has_box[(size_t)r] ? std::min(boxes[(size_t)r][(size_t)k], bx[k]) : bx[k];
+                        boxes[(size_t)r][(size_t)k + 3] = has_box[(size_t)r] ? std::max(boxes[(size_t)r][(size_t)k + 3], bx[k + 3]) : bx[k + 3];
+                    }
+                    has_box[(size_t)r] = 1;
+                }
+                nact[(size_t)r] += (int64_t)m->rec_end - (int64_t)m->rec_begin;
+                nchunks[(size_t)r] += m->g.nchunks;
+                if (m->from_signs) from_signs[(size_t)r] = 1;
+                for (int k = 0; k < 4; k++) stage_ms[(size_t)r][(size_t)k] += m->ms[k];
             }
-            m->vox = nullptr;
-            mesh_free_device(m);
-            delete m;
-            voxels_free(v);
+            if (g_trace) fprintf(stderr, "[sdfk] dev %d layers [%d,%d) in %d sub-slab(s): classified %.3f barrier %.3f done %.3f ms, %lld vertices\n", r, kb, ke,
+                                 (int)subs.size(), t_classified, t_barrier, wr.ms(), (long long)nv[(size_t)r]);
+        }
+        {
+            Lock l(d);
+            for (auto& sb : subs) {
+                if (sb.m) { sb.m->vox = nullptr; mesh_free_device(sb.m); delete sb.m; }
+                if (sb.v) voxels_free(sb.v);
+            }
         }
         return rr;
     });

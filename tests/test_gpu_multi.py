@@ -82,6 +82,20 @@ def test_multi_to_mesh_equals_single_gpu_and_oracle(sk, oracle, ctx1, mctx, name
     assert np.array_equal(bits(many.Normals), bits(om.normals))
 
 
+@pytest.mark.parametrize("cap", [1, 5, 17])
+def test_multi_to_mesh_with_several_sub_slabs_per_device(sk, ctx1, mctx, monkeypatch, cap):
+    """A device's layer range is meshed in sub-slabs (32-bit cell ids bound one job to 2^32 cells: 2048^3 on 2 devices needs
+    them); forced here on a small grid."""
+    expr, mn, mx = scene("readme")
+    one = sk.GpuSdf(expr, ctx=ctx1).ToMesh(mn, mx, 80, 64, 72)
+    monkeypatch.setenv("SDFK_SUBSLAB_CAP", str(cap))
+    many = sk.GpuSdf(expr, ctx=mctx).ToMesh(mn, mx, 80, 64, 72)
+    same_mesh(many, one, "sub-slab cap %d on %d devices" % (cap, mctx.device_count()))
+    stepped = sk.GpuSdf(expr, ctx=mctx).ToMesh(mn, mx, 80, 64, 72, step=2, isoValue=0.05)
+    monkeypatch.delenv("SDFK_SUBSLAB_CAP")
+    same_mesh(stepped, sk.GpuSdf(expr, ctx=ctx1).ToMesh(mn, mx, 80, 64, 72, step=2, isoValue=0.05), "sub-slabs, step 2")
+
+
 @pytest.mark.parametrize("name,dims", [("readme", (96, 96, 96)), ("perf", (50, 37, 29)), ("sphere", (40, 40, 3)), ("readme", (260, 9, 7))])
 def test_sharded_voxels_and_mesh_equal_single_gpu(sk, oracle, ctx1, mctx, name, dims):
     """sdfk_voxels_sample on a multi context shards by z-slab; export, clip, resample and sdfk_mesh_create on the shards give

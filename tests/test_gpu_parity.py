@@ -376,7 +376,8 @@ def test_cost_balanced_slabs_equal_single_gpu(sk):
 
 
 @pytest.mark.parametrize("name,dims,step", [("readme", (64, 64, 64), 1), ("perf", (50, 37, 29), 1), ("csg50", (96, 96, 48), 1),
-                                            ("readme", (72, 72, 72), 2)])
+                                            ("readme", (72, 72, 72), 2),
+                                            ("readme", (256, 40, 70), 1), ("csg50", (512, 24, 33), 1), ("perf", (256, 9, 5), 2)])   # rows of whole tile pairs: the 8-voxels-per-lane sampler
 def test_fused_to_mesh_equals_voxels_to_mesh(sk, oracle, name, dims, step):
     """Sdf.ToMesh samples distances only and evaluates vertex colours from the SDF: the mesh must be
     identical to the one made from fully materialised Voxels -- and to the oracle's."""
@@ -393,6 +394,28 @@ def test_fused_to_mesh_equals_voxels_to_mesh(sk, oracle, name, dims, step):
     ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, threads=4)
     om = oracle.marching_cubes(ov, oc, np.float32(mn), np.float32(mx), step=step)
     assert_mesh_equal(fused, om, "fused %s" % name)
+
+
+@pytest.mark.parametrize("dims,clip", [((256, 33, 70), True), ((512, 5, 40), False), ((256, 3, 3), True)])
+def test_distance_only_sampler_8_per_lane_values_and_sign_blocks(sk, oracle, dims, clip):
+    """sdfk_k_sample_dist8 (rows of whole tile pairs): distances equal the oracle's, and meshing from its sign blocks equals
+    meshing from the distances."""
+    from sdfkit_b200 import _native as N, scenes
+    expr, mn, mx = scenes.readme_scene()
+    nx, ny, nz = dims
+    sdf = expr.ToSdf()
+    v = sk.Voxels._sample(sdf, mn, mx, nx, ny, nz, clip=clip, colors=False)
+    ov, oc = oracle.to_voxels(sdf.lowered, np.float32(mn), np.float32(mx), nx, ny, nz, clip_to_bounds=clip, threads=4)
+    assert_bits_equal(v.Values, ov, "distances %s" % (dims,))
+    a = v.ToMesh()
+    sdf.ctx.set_option(N.OPT_SIGN_PLANES, 0)
+    try:
+        v2 = sk.Voxels._sample(sdf, mn, mx, nx, ny, nz, clip=clip, colors=False)
+        b = v2.ToMesh()
+    finally:
+        sdf.ctx.set_option(N.OPT_SIGN_PLANES, 1)
+    assert np.array_equal(a.Triangles, b.Triangles) and np.array_equal(bits(a.Vertices), bits(b.Vertices))
+    assert np.array_equal(bits(a.Colors), bits(b.Colors)) and np.array_equal(bits(a.Normals), bits(b.Normals))
 
 
 def test_distance_only_voxels_refuse_colors(sk):
