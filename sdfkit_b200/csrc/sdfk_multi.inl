@@ -301,12 +301,12 @@ extern "C" int sdfk_plan_layers(sdfk_ctx* c, sdfk_sdf* s, const float mn[3], con
 // ------------------------------------------------------------------------------------------------
 // SDF: the same cubin loaded on every device
 // ------------------------------------------------------------------------------------------------
-static int multi_sdf_load(sdfk_ctx* c, sdfk_sdf* s0, const std::vector<char>& cubin)
+static int multi_sdf_load(sdfk_ctx* c, sdfk_sdf* s0, const std::vector<char>& cubin, bool has_dist8)
 {
     s0->parts.assign(1, s0);
     for (size_t r = 1; r < c->devs.size(); r++) {
         sdfk_sdf* sr = nullptr;
-        int rc = sdf_load(c->devs[r], cubin, &sr);
+        int rc = sdf_load(c->devs[r], cubin, &sr, has_dist8);
         if (rc) {
             for (size_t q = 1; q < s0->parts.size(); q++) sdfk_sdf_destroy(s0->parts[q]);
             s0->parts.clear();
