@@ -83,24 +83,43 @@ def golden_digest(scene, n):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed regions: through NVML in this process (nvidia_ml_py; a query
+    costs microseconds), falling back to spawning nvidia-smi -- whose start-up holds a driver lock for milliseconds, which
+    showed as 8 - 35 ms outliers in the wall-clock-timed e2e steps (round 1 and the first round-2 runs)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & b else "Not Active" for _, b in self.BITS])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.5)        # (an nvidia-smi query holds a driver lock for milliseconds: keep them rare)
+            self._stop_evt.wait(0.05 if self.nvml is not None else 0.5)
 
     def stop(self):
         self._stop_evt.set()
@@ -110,7 +129,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -415,10 +434,10 @@ def strong_record(sk, expr, mn, mx, n, ndevs, steps, single_mesh_sha, scene, con
             del m
             vox.Dispose()
             e2e = []
-            for it in range(3 + steps):
+            for it in range(5 + steps):
                 t0 = time.perf_counter()
                 mesh = sdf.ToMesh(mn, mx, n, n, n)
-                if it >= 3:
+                if it >= 5:
                     e2e.append((time.perf_counter() - t0) * 1e3)
             sha_e2e = mesh_sha(mesh)
             d2h = mesh.Vertices.nbytes * 3 + mesh.Triangles.nbytes
@@ -645,7 +664,7 @@ def run_ours(args):
         e_times = []
         d2h = 0
         if world == 1:
-            for _ in range(2):                                   # warm: device + pinned host pools reach steady state
+            for _ in range(max(args.warmup, 5)):                 # warm: device + pinned host pools reach steady state
                 mesh = sdf.ToMesh(mn, mx, n, n, n)               # (two result sets are alive while `mesh = sdf.ToMesh()` runs)
             torch.cuda.synchronize()
             e0 = time.perf_counter()
@@ -673,7 +692,7 @@ def run_ours(args):
                 offs, _ = ejob.offsets(allc)
                 parts = ejob.emit_host(offs)
                 return sum(m.Vertices.nbytes * 3 + m.Triangles.nbytes + 24 for m in parts)
-            for _ in range(3):
+            for _ in range(max(args.warmup, 5)):
                 e2e_step()
             barrier()
             e0 = time.perf_counter()
