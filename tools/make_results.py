@@ -1,12 +1,12 @@
 #!/usr/bin/env python3
-"""Regenerates RESULTS.md from the measured JSON lines under profiles/.  usage: python tools/make_results.py [tag]"""
+"""Regenerates RESULTS.md from the measured JSON lines under profiles/ (tools/measure_round.sh, tools/measure_multi.sh,
+tools/summarise_round.sh).  usage: python tools/make_results.py [tag]"""
 import json
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01s4"
-late = sys.argv[2] if len(sys.argv) > 2 else "r01s5"        # a later 1-GPU run (kernels only got faster; its box had slower PCIe)
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 P = os.path.join(ROOT, "profiles")
 
 
@@ -15,95 +15,119 @@ def load(name):
     return json.load(open(path)) if os.path.exists(path) else None
 
 
-d = load(tag + "_bench_1gpu.json")
-last = load("r01s6_bench_1gpu.json")                          # the very last bench.py run of the session
-multi = {n: (load("%s_bench_%dgpu.json" % (tag, n)) or load("r01s4_bench_%dgpu.json" % n)) for n in (2, 4, 8)}
-cfg = [json.loads(l) for l in open(os.path.join(P, late + "_configs.txt")) if l.startswith("{")]
-d5 = load(late + "_bench_1gpu.json")
-st = d5["stages_ms"]
-FP32 = 3.49e13
-
-
-def bench_row(n, x):
-    if x is None:
-        return ""
-    g = x["config"]["grid"][0]
+B = {n: load("%s_bench_%dgpu.json" % (tag, n)) for n in (1, 2, 4, 8)}
+ref = load(tag + "_bench_reference.json")
+r1 = load("r01s6_bench_1gpu.json")
+d = B[1]
+st = d["stages_ms"]
+cfg = d["configs"]
+c3, c5 = cfg["config3_csg50_1024"], cfg["config5_toimage_1080p"]
+exp = cfg["voxels_export"]
+S = (B[8] or d)["strong_1024"]
+cpu = d["cpu_baseline"]
+out = []
+w = out.append
+w("# RESULTS -- round 2 (measured on boxes of the pool, NVIDIA B200, SM clock %s MHz under load, throttle reasons: %s)\n" % (
+    d["clocks"]["sm_mhz"], d["clocks"]["reasons"] or "none"))
+w("All GPU numbers: CUDA events on the library's stream after >= 5 warm-ups (wall clock where a call returns a host result); parity mode\n"
+  "(IEEE f32/f64, no FMA contraction), every output bit-exact against the CPU oracle and the committed golden fixtures in the GPU\n"
+  "test-suite (177 tests on one GPU, 178 with two). CPU numbers: the C++ restatement of the reference's CPU path (`oracle/`, g++ -O2\n"
+  "-ffp-contract=off) on the box's %d host cores, on a bounded sample of the same workload -- the .NET reference itself cannot run here.\n"
+  "Raw lines and ncu summaries: `profiles/%s_*` (`profiles/CHANGELOG.md`). Roofline denominators: HBM %.0f GB/s (measured copy,\n"
+  "`MEASURED_PEAKS.json`; a pure store stream can exceed a copy's read+write rate, hence fractions slightly above 1); FP32 without FMA\n"
+  "%.3g lane-op/s (measured FMUL+FADD chains, `profiles/fp32_peak.json`). Regenerate: `python tools/make_results.py %s`.\n" % (
+      cpu["cores"], tag, d["roofline"]["peak"], c3["roofline"]["peak"] * 1e12, tag))
+w("## bench.py (README RepeatXY scene -> Voxels (clip) -> MarchingCubes; one step = sample 16 B/voxel + mesh)\n")
+w("Weak scaling, one process per GPU under torchrun, NCCL count all-gather (what the driver runs):\n")
+w("| GPUs | grid | ms/step | voxels/s (whole job) | tris/s | K1 fraction of HBM peak | fused `Sdf.ToMesh` step (device) | e2e `Sdf.ToMesh`, mesh in host memory (mean / median) | parity_check |")
+w("|---|---|---|---|---|---|---|---|---|")
+for n in (1, 2, 4, 8):
+    x = B[n]
+    if not x:
+        continue
     e = x["e2e"]
-    return "| %d | %d³ | %.2f | %.3g | %.3g | %.2f ms = %.3g voxels/s | %.2f ms = %.3g voxels/s (%.0f MB D2H per step) |\n" % (
-        n, g, x["ms_per_step"], x["value"], x["tris_per_s"], x["fused_to_mesh"]["ms_per_step"], x["fused_to_mesh"]["value"],
-        e["ms_per_step"], e["value"], e["d2h_bytes_per_step"] / 1e6)
-
-
-txt = """# RESULTS — round 1 (measured on boxes of the pool, NVIDIA B200, SM clock 1965 MHz, no throttle reasons)
-
-All GPU numbers: CUDA events on the library's stream, after ≥ 3 warm-ups; parity mode (IEEE f32/f64, no FMA contraction),
-every output bit-exact against the CPU oracle and the committed golden fixtures in the GPU test-suite (113 tests, incl.
-512³ / 1024³ property tests and exhaustive 2^32 checks of the packed sqrt / constant division). CPU numbers: the C++
-restatement of the reference's CPU path (`oracle/`, g++ -O2 -ffp-contract=off) on the box's 16 host cores, on a bounded
-sample of the same workload — the .NET reference itself cannot run here. Raw lines and ncu summaries: `profiles/%s_*`
-(`profiles/r01_*`, `r01s2_*` are earlier snapshots of the round). Roofline denominators: HBM 6553 GB/s (measured copy,
-`MEASURED_PEAKS.json`); FP32 without FMA 3.49e13 lane-op/s (measured FMUL+FADD chains). Box-to-box spread: ±2 %% on kernels; the e2e
-call follows the box's PCIe (observed over the session: 6.2 – 6.5 ms on most boxes, 7.5 ms on one). The table below is the `%s` snapshot
-(all four GPU counts within the same hour); stage times and the configuration table are from the last run of the session (`%s`:
-step %.2f ms, fused step %.2f ms, e2e %.2f ms on a box with slower PCIe). The last `bench.py` run of the session (`r01s6`, all changes
-in): step %.2f ms = %.3g voxels/s, fused step %.2f ms, e2e %.2f ms = %.3g voxels/s, K1 at %.2f of the HBM peak. (regenerate with `python tools/make_results.py %s`)
-
-## bench.py (README RepeatXY scene → Voxels (clip) → MarchingCubes; one step = sample + mesh)
-
-| GPUs | grid | ms/step | voxels/s (whole job) | tris/s | fused `Sdf.ToMesh` step (device) | e2e `Sdf.ToMesh` (mesh in host memory) |
-|---|---|---|---|---|---|---|
-""" % (tag, tag, late, d5["ms_per_step"], d5["fused_to_mesh"]["ms_per_step"], d5["e2e"]["ms_per_step"],
-       last["ms_per_step"], last["value"], last["fused_to_mesh"]["ms_per_step"], last["e2e"]["ms_per_step"], last["e2e"]["value"], last["roofline"]["frac"], tag)
-txt += bench_row(1, d)
-for n in (2, 4, 8):
-    txt += bench_row(n, multi[n])
-cb = d["cpu_baseline"]
-txt += """
-Weak scaling of the step: 1 → 8 GPUs = %.2f× (8-GPU line: %s). The multi-GPU e2e number is bounded by the host side of the box (a
-32-vCPU, single-NUMA-node VM): 8 ranks streaming their shares concurrently reach ≈ 91 GB/s in total (937 MB in 10.3 ms), against
-55 GB/s for one GPU alone; up to 4 GPUs every rank still gets its full link (e2e 5.9–6.4 ms).
-
-CPU restatement on a 256³ sample (16 cores sampling, 1 thread meshing, like the reference): %.3g voxels/s for the step
-(sampling alone %.2g voxels/s, meshing %.2g tris/s) → the 1-GPU step is ≈ %s× the CPU step, the e2e call ≈ %s×.
-
-Stage times at 1024³ on one GPU (ms): K1 sample %.2f · K2' classify (sign blocks) %.2f · K3 scan 2 × %.2f · K4a compact %.2f · K4b emit %.2f
-(triangle kernel 0.15 + vertex kernel 0.44). ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (K1 72 %%, emit
-16.4 %%, compact 5.4 %%, classify 3.7 %%, scans 2 %% — the same shares as the event-timed stages).
-
-| kernel | algorithmic bytes | time | achieved | fraction of measured HBM peak |
-|---|---|---|---|---|
-| K1 `sdfk_k_sample` | 16 B × 1.07e9 voxels = 17.18 GB written (ncu: 17.31 GB DRAM writes incl. 134 MB of sign blocks, 6 MB reads) | %.2f ms | %.2f TB/s | **%.2f** |
-| K1d `sdfk_k_sample_dist` | 4 B × 1.07e9 = 4.29 GB written (ncu: 4.37 GB) | 0.90 ms | 4.8 TB/s | 0.73 (instruction-issue bound: 83 %% issue-active) |
-| K2' `mc_classify_signs` | 1 bit × 1.07e9 = 134 MB read (ncu: 146 MB) | 0.14 ms | — | replaces K2's 4.29 GB pass (0.86 ms, 0.76 of peak) |
-| K4b `mc_emit_verts` | 36 B × 3.9e6 vertices written + ≤ 4 × 8 corner reads (ncu: 1.0 GB read, 0.2 GB written) | 0.44 ms | — | latency-bound (≈ 32 %% issue-active, 28 of 32 lanes) |
-
-History of the round (1024³, one GPU, ms/step): first correct path 16.4 → z-column sampling + batched MC loads 7.5 → emit
-unrolled / 32-byte records 6.7 → classify counts only active cells 5.8 → lane-per-active-cell compact 5.3 → 5.2 → sign blocks
-(K2 0.86 → K2' 0.14) 4.27 → emit split into triangle + kind-sorted vertex kernels, table-driven gathers (0.93 → 0.63), compact at
-4 CTAs/SM, second scan over active chunks only (0.175 → 0.087) → %.2f.
-e2e `Sdf.ToMesh`: 64 (pageable host buffers) → 9.6 (pinned) → 7.6 (distance-only voxels) → 6.0–6.5 (z-slab pipeline, chunked emit,
-streamed downloads; 4.3 ms of it is the 234 MB over PCIe).
-
-## The five BASELINE.json configurations (one GPU; `profiles/%s_configs.txt`)
-
-| config | GPU | CPU restatement (bounded sample, 16 cores) |
-|---|---|---|
-""" % (multi[8]["value"] / d["value"] if multi[8] else 0, "`profiles/%s_bench_8gpu.json`" % tag, cb["value"], cb["detail"]["sample_voxels_per_s"],
-       cb["detail"]["mesh_tris_per_s"], "{:,.0f}".format(d["value"] / cb["value"]), "{:,.0f}".format(d["e2e"]["value"] / cb["value"]),
-       st["sample_ms"], st["classify_ms"], st["scan_ms"] / 2, st["compact_ms"], st["emit_ms"], late,
-       st["sample_ms"], d5["roofline"]["achieved"] / 1e3, d5["roofline"]["frac"], d5["ms_per_step"], late)
-for x in cfg:
-    if "render_ms" in x:
-        txt += "| %s | %.3f ms = %.3g pixels/s = %.3g SDF evals/s = %.3g FP32 op/s (%.2f of the no-FMA FP32 rate) | %d×%d: %.3g pixels/s |\n" % (
-            x["config"], x["render_ms"], x["pixels_per_s"], x["sdf_evals_per_s"], x["fp32_ops_per_s"], x["fp32_ops_per_s"] / FP32,
-            x["cpu_image"][0], x["cpu_image"][1], x["cpu_pixels_per_s"])
-    else:
-        extra = "; %.2f of the no-FMA FP32 rate" % (x["samples_per_s"] * x["sdf_flops_per_sample"] / FP32) if x["sdf_flops_per_sample"] > 100 else ""
-        txt += "| %s | sample %.2f ms = %.3g voxels/s (%.2f of HBM peak%s); mesh %.2f ms = %.3g tris/s, %.3g cells/s; %s triangles | %d³: sample %.3g voxels/s; mesh %.3g tris/s |\n" % (
-            x["config"], x["sample_ms"], x["samples_per_s"], x["sample_frac_hbm"], extra, x["mesh_ms"], x["tris_per_s"], x["cells_per_s"],
-            "{:,}".format(x["triangles"]), x["cpu_grid"], x["cpu_samples_per_s"], x["cpu_tris_per_s"])
-if multi[8]:
-    txt += "| 4: README scene 2048³ over 8 GPUs | %.2f ms/step, %.3g voxels/s, %.3g tris/s (`profiles/%s_bench_8gpu.json`) | no CPU counterpart (int32 / array limits of the reference) |\n" % (
-        multi[8]["ms_per_step"], multi[8]["value"], multi[8]["tris_per_s"], tag)
-open(os.path.join(ROOT, "RESULTS.md"), "w").write(txt)
-print(txt)
+    pc = x.get("parity_check")
+    w("| %d | %d^3 | %.2f | %.3g | %.3g | %.2f | %.2f ms | %.2f / %.2f ms = %.3g voxels/s (%.0f MB D2H) | %s |" % (
+        n, x["config"]["grid"][0], x["ms_per_step"], x["value"], x["tris_per_s"], x["roofline"]["frac"], x["fused_to_mesh"]["ms_per_step"],
+        e["ms_per_step"], e["ms_per_step_median"], e["value"], e["d2h_bytes_per_step"] / 1e6,
+        "n/a (one GPU)" if not pc else ("ok: shares == 1-GPU mesh and golden digest, slab boundaries == oracle (%d voxels), gather %.0f GB/s" % (
+            pc["slab_boundaries_vs_oracle"]["voxels_checked"], pc["mesh_gather"]["gbs"]) if pc["ok"] else "FAILED")))
+if B[8]:
+    w("\nWeak scaling of the step, 1 -> 8 GPUs: %.2fx the throughput (efficiency %.2f). The multi-GPU e2e number is bounded by the host side of the\n"
+      "box: devices copying to page-locked memory at the same time reach %s GB/s in total (`strong_1024.pcie_d2h_aggregate_gbs`, 1/2/4/8 devices),\n"
+      "so the %.0f MB of the 2048^3 mesh cannot land in less than %.1f ms.\n" % (
+          B[8]["value"] / d["value"], B[8]["value"] / d["value"] / 8,
+          " / ".join("%.0f" % S["pcie_d2h_aggregate_gbs"][k] for k in sorted(S["pcie_d2h_aggregate_gbs"], key=int)),
+          B[8]["e2e"]["d2h_bytes_per_step"] / 1e6, B[8]["e2e"]["d2h_bytes_per_step"] / 1e6 / S["pcie_d2h_aggregate_gbs"]["8"]))
+w("Strong scaling at 1024^3 through the multi-GPU context of the C ABI (`sdfk_ctx_create_multi`: one process, N devices, results checked\n"
+  "against the single-GPU digest in every run; wall clock from call to completion on all devices):\n")
+w("| devices | Voxels (16 B/voxel) + MarchingCubes, device resident | speed-up | e2e `Sdf.ToMesh`, ONE host mesh (234 MB) | speed-up | `ToImage` 1920x1080, row bands, host image | config 4: 2048^3 `Sdf.ToMesh` (937 MB host mesh) |")
+w("|---|---|---|---|---|---|---|")
+for k in sorted(S["by_devices"], key=int):
+    v = S["by_devices"][k]
+    c4 = v.get("config4_2048")
+    w("| %s | %.2f ms = %.3g voxels/s | %.2fx | %.2f ms | %.2fx | %.2f ms | %s |" % (
+        k, v["device_step_wall_ms"], v["voxels_per_s"], v["speedup_device_step"], v["e2e_ms"], v["speedup_e2e"], v["toimage_1080p_ms"],
+        "--" if not c4 else ("%.1f ms, digest == golden: %s" % (c4["e2e_ms"], c4.get("equal_to_golden_digest")) if "e2e_ms" in c4 else c4.get("error", "")[:60])))
+w("\nCPU restatement on a %d^3 sample (%d cores sampling, 1 thread meshing, like the reference): %.3g voxels/s for the step (sampling alone %.3g voxels/s,\n"
+  "meshing %.3g tris/s) -> the 1-GPU step is ~ %.0fx the CPU step's rate, the e2e call ~ %.0fx.  The reference arm (`bench.py --impl reference`)\n"
+  "prints the grid it measured (%s, warm-up %d, %d steps) and `same_config: false`.\n" % (
+      cpu["detail"]["grid"][0], cpu["cores"], cpu["value"], cpu["detail"]["sample_voxels_per_s"], cpu["detail"]["mesh_tris_per_s"],
+      d["value"] / cpu["value"], d["e2e"]["value"] / cpu["value"], "x".join(str(g) for g in ref["config"]["grid"]), ref["warmup"], ref["steps"]))
+w("Stage times at 1024^3 on one GPU (ms): K1 sample %.2f | K2' classify (sign blocks) %.2f | K3 scans %.2f | K4a compact %.2f | K4b emit %.2f (triangles 0.15 + vertices 0.39).\n"
+  "ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (the same shares as the event-timed stages).\n" % (
+      st["sample_ms"], st["classify_ms"], st["scan_ms"], st["compact_ms"], st["emit_ms"], tag))
+rm = d["roofline_mesh"]
+w("| kernel | algorithmic bytes / flops | time | achieved | fraction of roofline | round 1 |")
+w("|---|---|---|---|---|---|")
+w("| K1 `sdfk_k_sample` (README) | 16 B x 1.07e9 voxels = 17.18 GB written (ncu: 17.17 GB DRAM writes, 0.4 MB reads) | %.2f ms | %.0f GB/s | **%.2f** of HBM | 2.70 ms, 0.97 |" % (
+    st["sample_ms"], d["roofline"]["achieved"], d["roofline"]["frac"]))
+w("| K1 `sdfk_k_sample` (CSG-50, config 3) | 205 IEEE f32 ops x 1.07e9 voxels | %.2f ms | %.1f Top/s | **%.2f** of the no-FMA FP32 rate (%.2f of HBM) | 10.82 ms, 0.58 |" % (
+    c3["sample_ms"], c3["roofline"]["achieved"], c3["roofline"]["frac"], c3["roofline"]["hbm_frac"]))
+w("| K1d `sdfk_k_sample_dist8` | 4 B x 1.07e9 = 4.29 GB written | 0.684 ms | 6.28 TB/s | **0.96** of HBM | 0.81 ms, 0.81 |")
+w("| K2'-K4b meshing (sum) | SURVEY 8(d): %.2f GB; sign-block formulation: %.2f GB | %.2f ms | %.3g tris/s, %.3g cells/s | %.2f of HBM by 8(d)'s bytes, %.2f by the bytes really needed (latency-bound gathers over 0.4 %% of the cells) | 1.02 ms |" % (
+    rm["algorithmic_bytes_8d"] / 1e9, rm["algorithmic_bytes_sign_blocks"] / 1e9, rm["ms"], rm["tris_per_s"], rm["cells_per_s"], rm["frac_8d"], rm["frac_sign_blocks"]))
+k5 = c5["readme"]
+w("| K5 `sdfk_k_render` (README, 1080p) | %d IEEE ops/pixel | %.3f ms | %.1f Top/s | **%.2f** of the no-FMA FP32 rate | 0.189 ms, 0.35 |" % (
+    k5["roofline"]["ops_per_pixel"], k5["kernel_ms"], k5["roofline"]["achieved"], k5["roofline"]["frac"]))
+k5p = c5["perf_program"]
+w("| K5 `sdfk_k_render` (Perf/Program.cs scene, 1080p) | %d IEEE ops/pixel | %.3f ms | %.1f Top/s | %.2f | 0.490 ms, 0.30 |" % (
+    k5p["roofline"]["ops_per_pixel"], k5p["kernel_ms"], k5p["roofline"]["achieved"], k5p["roofline"]["frac"]))
+w("\n## The BASELINE.json configurations (sub-records of the N = 1 line, so the driver witnesses them)\n")
+w("| config | GPU | CPU restatement (bounded sample) |")
+w("|---|---|---|")
+w("| 2': README RepeatXY 1024^3 (bench workload) | step %.2f ms = %.3g voxels/s, %.3g tris/s; e2e `Sdf.ToMesh` %.2f ms | %d^3: %.3g voxels/s (step), %.3g tris/s |" % (
+    d["ms_per_step"], d["value"], d["tris_per_s"], d["e2e"]["ms_per_step"], cpu["detail"]["grid"][0], cpu["value"], cpu["detail"]["mesh_tris_per_s"]))
+w("| 3: CSG-50 1024^3 (50 builder nodes, 205 ops/sample) | sample %.2f ms = %.3g voxels/s (%.2f of the FP32 rate); mesh %.2f ms; step %.2f ms; %d triangles; e2e `Sdf.ToMesh` %.2f ms | 256^3: %.3g voxels/s (step) |" % (
+    c3["sample_ms"], c3["samples_per_s"], c3["roofline"]["frac"], c3["mesh_ms"], c3["ms_per_step"], c3["triangles"], c3["e2e"]["ms_per_step"],
+    c3.get("cpu_baseline", {}).get("value", float("nan"))))
+w("| 4: README scene 2048^3 over 2 / 4 / 8 GPUs | weak-scaling line above (8 ranks: %.2f ms/step, parity ok) and `Sdf.ToMesh` through the multi-GPU context (table above) | no CPU counterpart (int32 / array limits of the reference) |" % (
+    B[8]["ms_per_step"] if B[8] else float("nan")))
+for key, name in (("readme", "5: ToImage 1920x1080 README scene"), ("perf_program", "5': ToImage 1920x1080 Perf/Program.cs scene")):
+    v = c5[key]
+    w("| %s | protocol of `Perf/Program.cs:43-65` (3 loops through the public API, first discarded, host image): loops %s ms -> %.2f ms/image = %.3g pixels/s; kernel alone %.3f ms = %.3g SDF evals/s | 480x270: %.3g pixels/s |" % (
+        name, ", ".join("%.2f" % t for t in v["loops_ms"]), v["ms_per_image"], v["pixels_per_s"], v["kernel_ms"], v["sdf_evals_per_s"],
+        v.get("cpu_baseline", {}).get("value", float("nan"))))
+w("| `Voxels.Values` + `Colors` to host (C# layout) | 512^3: %.1f ms = %.1f GB/s; 1024^3 (17.2 GB): %.0f ms = %.1f GB/s = %.2f of the link's plain copy rate (%.1f GB/s) | -- |" % (
+    exp["grids"]["512"]["ms"], exp["grids"]["512"]["gbs"], exp["grids"]["1024"].get("ms", float("nan")), exp["grids"]["1024"].get("gbs", float("nan")),
+    exp["grids"]["1024"].get("frac_of_link", float("nan")), exp["pcie_d2h_gbs_plain_copy"]))
+w("\n## Round 2 against round 1 (same boxes, same protocol)\n")
+w("| | round 1 | round 2 |")
+w("|---|---|---|")
+if r1:
+    w("| 1-GPU step 1024^3 | %.2f ms | %.2f ms |" % (r1["ms_per_step"], d["ms_per_step"]))
+    w("| fused `Sdf.ToMesh` step (device) | %.2f ms | %.2f ms |" % (r1["fused_to_mesh"]["ms_per_step"], d["fused_to_mesh"]["ms_per_step"]))
+    w("| e2e `Sdf.ToMesh` 1024^3 (mean over the timed steps) | %.2f ms (driver: 8.78 mean / 6.02 median) | %.2f ms (max %.2f) |" % (
+        r1["e2e"]["ms_per_step"], d["e2e"]["ms_per_step"], d["e2e"]["ms_per_step_max"]))
+w("| CSG-50 sampling 1024^3 | 10.82 ms (0.58 of FP32) | %.2f ms (%.2f) |" % (c3["sample_ms"], c3["roofline"]["frac"]))
+w("| K1d distance-only sampling | 0.81 ms | 0.684 ms |")
+w("| `ToImage` 1080p kernel (README) | 0.189 ms | %.3f ms |" % k5["kernel_ms"])
+w("| `mc_emit_verts` | 0.44 ms | 0.39 ms |")
+w("| 1024^3 on 8 GPUs (strong) | not available | %.2f ms device step, %.2f ms e2e |" % (S["by_devices"].get("8", {}).get("device_step_wall_ms", float("nan")), S["by_devices"].get("8", {}).get("e2e_ms", float("nan"))))
+w("| weak scaling 1 -> 8 GPUs | 7.6x (N=4 efficiency 0.88) | %.2fx |" % ((B[8]["value"] / d["value"]) if B[8] else float("nan")))
+w("| reference arm | 384^3 labelled as 1024^3 | 512^3, labelled as measured, `same_config: false` |")
+w("\nParity unpinned by the reference's own tests (vertex positions / normals / colours, triangle order, the ambiguous Lewiner\n"
+  "branches, colour renders): the oracle restatement is the only authority there (DESIGN.md section 6); GPU and oracle agree bit for bit\n"
+  "on white noise (all 14 cases incl. centre vertices) and on every scene above.\n")
+open(os.path.join(ROOT, "RESULTS.md"), "w").write("\n".join(out))
+print("RESULTS.md written")
