@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdfk.so")
+# SDFK_LIB: another build of the same library (kernel A/B experiments: `python -m sdfkit_b200.build --variant name -DX=..`)
+LIB_PATH = os.environ.get("SDFK_LIB") or os.path.join(_HERE, "libsdfk.so")
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_float, C.c_void_p)
 _fp = C.POINTER(C.c_float)

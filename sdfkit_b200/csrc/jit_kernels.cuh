@@ -44,6 +44,21 @@ struct sdfk_sample8_params {
 
 #define SDFK_SAMPLE_WARPS 8
 
+// cache policy of the voxel / sign-block stores (the field is write-once): 0 = st.global.cs (evict-first), 1 = default
+// (write-back), 2 = st.global.cg, 3 = st.global.wt
+#ifndef SDFK_STORE_POLICY
+#define SDFK_STORE_POLICY 0
+#endif
+#if SDFK_STORE_POLICY == 0
+#define SDFK_ST(p, v) __stcs(p, v)
+#elif SDFK_STORE_POLICY == 1
+#define SDFK_ST(p, v) (*(p) = (v))
+#elif SDFK_STORE_POLICY == 2
+#define SDFK_ST(p, v) __stcg(p, v)
+#else
+#define SDFK_ST(p, v) __stwt(p, v)
+#endif
+
 // Sign blocks: a by-product of sampling that lets marching cubes find the active cells without re-reading the
 // distance field (1 bit per voxel instead of 4 bytes).  A warp walks its column (128 x of one y) in z, so every lane
 // keeps the signs of its 4 voxels over 8 consecutive z slices in ONE register, four such registers make a uint4, and
@@ -140,7 +155,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
             }
             sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
             if (vec) {
-                if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
+                if (x0 < P.nx) SDFK_ST(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
                 st[lane * 3 + 0] = make_float4(c[0], c[1], c[2], c[3]);
                 st[lane * 3 + 1] = make_float4(c[4], c[5], c[6], c[7]);
                 st[lane * 3 + 2] = make_float4(c[8], c[9], c[10], c[11]);
@@ -149,7 +164,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     const int q = (int)lane + 32 * k;
-                    if (q < nq) __stcs(g + q, st[q]);
+                    if (q < nq) SDFK_ST(g + q, st[q]);
                 }
                 __syncwarp();
             } else {
@@ -168,7 +183,7 @@ sdfk_k_sample(const sdfk_sample_params P, float* __restrict__ dist, float* __res
         const int sq = (zb0 >> 3) & 3;
         if (sq == 0) sw.x = sacc; else if (sq == 1) sw.y = sacc; else if (sq == 2) sw.z = sacc; else sw.w = sacc;
         }
-        if (signs) __stcs(scol + (size_t)(zg0 >> 5) * 32u, sw);     // evict-first like the voxel stream (a second cache policy in the stream costs 3 %)
+        if (signs) SDFK_ST(scol + (size_t)(zg0 >> 5) * 32u, sw);     // evict-first like the voxel stream (a second cache policy in the stream costs 3 %)
         }
     }
 }
@@ -197,7 +212,7 @@ static __device__ __forceinline__ unsigned sdfk_sample_dist_block(const sdfk_sam
         }
         sacc |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
         if (vec) {
-            if (x0 < P.nx) __stcs(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
+            if (x0 < P.nx) SDFK_ST(reinterpret_cast<float4*>(dist + vbase) + lane, make_float4(d[0], d[1], d[2], d[3]));
         } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -262,7 +277,7 @@ sdfk_k_sample_dist(const sdfk_sample_params P, float* __restrict__ dist, uint4* 
         const int sq = (zb0 >> 3) & 3;
         if (sq == 0) sw.x = sacc; else if (sq == 1) sw.y = sacc; else if (sq == 2) sw.z = sacc; else sw.w = sacc;
         }
-        if (signs) __stcs(scol + (size_t)(zg0 >> 5) * 32u, sw);     // evict-first like the voxel stream (a second cache policy in the stream costs 3 %)
+        if (signs) SDFK_ST(scol + (size_t)(zg0 >> 5) * 32u, sw);     // evict-first like the voxel stream (a second cache policy in the stream costs 3 %)
         }
     }
 }
@@ -334,16 +349,16 @@ sdfk_k_sample_dist8(const sdfk_sample_params P, const sdfk_sample8_params Q, flo
                     sa |= sdfk_sign_nibble(d, P.sign_iso) << ssh;
                     sb |= sdfk_sign_nibble(d + 4, P.sign_iso) << ssh;
                     float4* const out = reinterpret_cast<float4*>(dist + vbase) + lane;
-                    __stcs(out, make_float4(d[0], d[1], d[2], d[3]));
-                    __stcs(out + 32, make_float4(d[4], d[5], d[6], d[7]));
+                    SDFK_ST(out, make_float4(d[0], d[1], d[2], d[3]));
+                    SDFK_ST(out + 32, make_float4(d[4], d[5], d[6], d[7]));
                 }
                 const int sq = (zb0 >> 3) & 3;
                 if (sq == 0) { swa.x = sa; swb.x = sb; } else if (sq == 1) { swa.y = sa; swb.y = sb; }
                 else if (sq == 2) { swa.z = sa; swb.z = sb; } else { swa.w = sa; swb.w = sb; }
             }
             if (signs) {
-                __stcs(scol + (size_t)(zg0 >> 5) * 32u, swa);
-                __stcs(scol + colwords + (size_t)(zg0 >> 5) * 32u, swb);
+                SDFK_ST(scol + (size_t)(zg0 >> 5) * 32u, swa);
+                SDFK_ST(scol + colwords + (size_t)(zg0 >> 5) * 32u, swb);
             }
         }
     }

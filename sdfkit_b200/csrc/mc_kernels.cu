@@ -63,6 +63,8 @@ __host__ __device__ static inline void mc_edge_corners(int e, int& a, int& b)
     b = B[e];
 }
 
+cudaError_t mc_init_kernels();     // per-device kernel attributes (below)
+
 cudaError_t mc_init_tables()
 {
     static unsigned leaf[256];
@@ -115,6 +117,7 @@ cudaError_t mc_init_tables()
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_cross, cross, sizeof(cross));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_meta, meta, sizeof(meta));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_quick, quick, sizeof(quick));
+    if (err == cudaSuccess) err = mc_init_kernels();
     return err;
 }
 
@@ -728,7 +731,8 @@ __device__ static inline void st_desc(uint4* p, uint4 v)
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, unsigned n, ScanWs* ws, McTotals* totals, unsigned write_every)
+mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, unsigned n, ScanWs* ws, McTotals* totals, unsigned write_every,
+               unsigned* __restrict__ alist)
 {
     __shared__ unsigned s_tile;
     __shared__ uint3 s_warp[SCAN_THREADS / 32];
@@ -805,12 +809,14 @@ mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, un
         // prefixes are only ever looked up for non-empty items (the lookups test the count first) and at multiples of
         // write_every (cell-layer boundaries): 99 % of the 16-byte stores of the first scan are skipped
         if (first + k < n && (c[k] != 0u || (first + k) % write_every == 0u)) base[first + k] = make_uint4(run.x, run.y, run.z, c[k]);
+        // first scan: the active chunks by rank (run.y counts them), so that K4a visits those only
+        if (alist && first + k < n && c[k] != 0u) alist[run.y] = first + k;
         run.x += MC_CNT_ACT(c[k]); run.y += MC_CNT_V(c[k]); run.z += MC_CNT_T(c[k]);
     }
 }
 
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
-                           McTotals* totals, unsigned write_every, cudaStream_t s)
+                           McTotals* totals, unsigned write_every, unsigned* alist, cudaStream_t s)
 {
     if (nchunks == 0) return cudaSuccess;                     // (the last tile always writes the totals otherwise)
     if (ws_bytes < mc_scan_workspace_bytes(nchunks)) return cudaErrorInvalidValue;
@@ -818,14 +824,16 @@ cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks
     if (err == cudaSuccess) err = cudaMemsetAsync(totals, 0, sizeof(McTotals), s);
     if (err != cudaSuccess) return err;
     const unsigned ntiles = (nchunks + SCAN_TILE - 1) / SCAN_TILE;
-    mc_scan_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(counts, base, nchunks, (ScanWs*)scan_ws, totals, write_every ? write_every : 1u);
+    mc_scan_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(counts, base, nchunks, (ScanWs*)scan_ws, totals, write_every ? write_every : 1u, alist);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4a mc_compact: one LANE per active cell.  A warp takes 32 consecutive chunks, lists their active cells (chunk
-// by chunk, cell order inside a chunk -- i.e. visiting order) from the activity masks K2 wrote, and hands one cell
-// to every lane: 8 corner loads, cube index, leaf (256-entry table; FP64 tests for the ambiguous cases), created
+// K4a mc_compact: one LANE per active cell.  A warp takes `ch` consecutive ACTIVE chunks (the list the first scan wrote:
+// 1 % of the chunks in the README scene -- walking all chunks cost 0.1 ms of dependent count loads), lists their active
+// cells (chunk by chunk, cell order inside a chunk -- i.e. visiting order) from the activity masks K2 wrote, and hands
+// one cell to every lane: 8 corner loads (scalar: fetching each row pair as one aligned 16-byte load + selects was
+// measured 50 % slower, 0.16 -> 0.25 ms), cube index, leaf (256-entry table; FP64 tests for the ambiguous cases), created
 // vertices / triangles, and a segmented warp scan that yields the cell's offsets inside its chunk.  Writes the
 // 32-byte record at base[chunk].x + (rank in chunk) and, per chunk, the full packed counts for the second scan.
 // ---------------------------------------------------------------------------------------------------
@@ -853,7 +861,7 @@ __device__ static inline unsigned long long mc_record_aux(unsigned leaf, int i, 
 #define MC_COMPACT_MINB 4
 #endif
 __global__ void __launch_bounds__(256, MC_COMPACT_MINB)
-mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned* __restrict__ counts,
+mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned* __restrict__ alist, unsigned nactive, unsigned ch,
                   const uint4* __restrict__ base, McRecord* __restrict__ recs, const uint4* __restrict__ masks,
                   unsigned* __restrict__ acounts)
 {
@@ -864,10 +872,18 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned nw = (gridDim.x * blockDim.x) >> 5;
     const float iso = g.iso;
-    for (unsigned c0 = gw * 32u; c0 < g.nchunks; c0 += nw * 32u) {
-        // lane L looks after chunk c0 + L
-        const unsigned myc = c0 + lane;
-        const unsigned nact = (myc < g.nchunks) ? MC_CNT_ACT(counts[myc]) : 0u;
+    for (unsigned r0 = gw * ch; r0 < nactive; r0 += nw * ch) {
+        // lane L < ch looks after the active chunk of rank r0 + L
+        const unsigned myr = r0 + lane;
+        unsigned myc = 0, nact = 0, myslot = 0;
+        uint4 mymask = make_uint4(0, 0, 0, 0);
+        if (lane < ch && myr < nactive) {
+            myc = alist[myr];
+            const uint4 b4 = base[myc];                           // x: first record slot, w: what the classifier counted
+            myslot = b4.x;
+            nact = MC_CNT_ACT(b4.w);
+            mymask = masks[myc];
+        }
         unsigned incl = nact;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -875,11 +891,7 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
             if (lane >= (unsigned)d) incl += t;
         }
         const unsigned total = __shfl_sync(FULL, incl, 31);
-        if (total == 0u) continue;
         const unsigned pre = incl - nact;                         // items of the chunks before mine
-        uint4 mymask = make_uint4(0, 0, 0, 0);
-        unsigned myslot = 0, myrank = 0;                          // first record slot / rank among the ACTIVE chunks
-        if (nact) { mymask = masks[myc]; const uint2 b2 = *reinterpret_cast<const uint2*>(base + myc); myslot = b2.x; myrank = b2.y; }
         unsigned carry = 0;                                       // packed counts of the leading chunk's items in earlier batches
         for (unsigned b = 0; b < total; b += 32u) {
             const unsigned t = b + lane;
@@ -893,7 +905,8 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
                 if (probe < 32u && v <= t) lo += (unsigned)step;
             }
             const unsigned src = valid ? min(lo, 31u) : 0u;
-            const unsigned spre = __shfl_sync(FULL, pre, src), snact = __shfl_sync(FULL, nact, src), sslot = __shfl_sync(FULL, myslot, src), srank = __shfl_sync(FULL, myrank, src);
+            const unsigned spre = __shfl_sync(FULL, pre, src), snact = __shfl_sync(FULL, nact, src), sslot = __shfl_sync(FULL, myslot, src);
+            const unsigned chunk = __shfl_sync(FULL, myc, src), srank = r0 + src;
             uint4 sm;
             sm.x = __shfl_sync(FULL, mymask.x, src); sm.y = __shfl_sync(FULL, mymask.y, src);
             sm.z = __shfl_sync(FULL, mymask.z, src); sm.w = __shfl_sync(FULL, mymask.w, src);
@@ -901,7 +914,6 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
             int i = 0, j = 0, kl = 0;
             if (valid) {
                 q = t - spre;                                     // rank of my cell among the chunk's active cells
-                const unsigned chunk = c0 + src;
                 const unsigned xc = chunk % (unsigned)g.cpr, row = chunk / (unsigned)g.cpr;
                 j = (int)(row % (unsigned)g.ncy);
                 kl = (int)(row / (unsigned)g.ncy);
@@ -949,17 +961,20 @@ mc_compact_kernel(const McGrid g, const float* __restrict__ dist, const unsigned
     }
 }
 
-cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* alist, unsigned nactive, const uint4* base,
                               McRecord* recs, const uint4* masks, unsigned* acounts, cudaStream_t s)
 {
-    if (g.nchunks == 0) return cudaSuccess;
+    if (g.nchunks == 0 || nactive == 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned groups = (g.nchunks + 31u) / 32u;
+    // chunks per warp: enough warp items to fill the machine twice over (a README chunk holds ~24 active cells)
+    unsigned ch = nactive / ((unsigned)sms * 128u);
+    ch = ch < 1u ? 1u : (ch > 32u ? 32u : ch);
+    const unsigned groups = (nactive + ch - 1u) / ch;
     unsigned blocks = (groups + 7u) / 8u;
     if (blocks > (unsigned)sms * 8u) blocks = (unsigned)sms * 8u;
-    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, counts, base, recs, masks, acounts);
+    mc_compact_kernel<<<blocks, 256, 0, s>>>(g, dist, alist, nactive, ch, base, recs, masks, acounts);
     return cudaGetLastError();
 }
 
@@ -1034,7 +1049,15 @@ __device__ static inline unsigned mc_float_key(float f)   // monotonic float -> 
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ static inline void mc_store_vertex(const McEmitParams& p, long long slot, McF3 pos, McF3 col, McF3 nsum, unsigned* lo, unsigned* hi,
+// where a block's vertices go, indexed by the local vertex index: rows staged in shared memory (MC_VERT_STAGE) or the output
+// arrays themselves at the block's first slot
+struct McStage {
+    float* v;      // positions, 3 floats per local vertex
+    float* c;      // colours (3 floats) -- or, for distance-only voxels, the (cell, edge) recipe (2 words)
+    float* n;      // normals
+};
+
+__device__ static inline void mc_store_vertex(const McEmitParams& p, const McStage& st, unsigned loc, McF3 pos, McF3 col, McF3 nsum, unsigned* lo, unsigned* hi,
                                              unsigned cell, unsigned edge)
 {
     // Cell.NegativeNormals (Cell.cs:97-109): -Vector3.Normalize(sum)
@@ -1051,12 +1074,14 @@ __device__ static inline void mc_store_vertex(const McEmitParams& p, long long s
         pos = tp;
         n.x = tn.x / l2; n.y = tn.y / l2; n.z = tn.z / l2;
     }
-    float* vo = p.verts + slot * 3;
-    float* co = p.cols + slot * 3;
-    float* no = p.nrms + slot * 3;
+#ifdef MC_VERT_DIAG_NOSTORE   /* diagnostic build only: how much of the kernel is its stores (results are wrong) */
+    if (pos.x != 123456.789f) return;
+#endif
+    float* vo = st.v + loc * 3u;
+    float* no = st.n + loc * 3u;
     vo[0] = pos.x; vo[1] = pos.y; vo[2] = pos.z;
-    if (p.rgb) { co[0] = col.x; co[1] = col.y; co[2] = col.z; }
-    else p.recipes[slot] = make_uint2(cell, edge);           // colours follow from sdfk_k_vertex_colors
+    if (p.rgb) { float* co = st.c + loc * 3u; co[0] = col.x; co[1] = col.y; co[2] = col.z; }
+    else { st.c[loc * 2u] = __uint_as_float(cell); st.c[loc * 2u + 1u] = __uint_as_float(edge); }   // colours follow from sdfk_k_vertex_colors
     no[0] = n.x; no[1] = n.y; no[2] = n.z;
     // Mesh.Measure (Mesh.cs:30-45), reduced per thread -> per warp -> one atomic per warp
     lo[0] = min(lo[0], mc_float_key(pos.x)); lo[1] = min(lo[1], mc_float_key(pos.y)); lo[2] = min(lo[2], mc_float_key(pos.z));
@@ -1141,7 +1166,7 @@ __device__ static inline void mc_gather_from(const McEmitParams& p, int ci, int 
 // (X,Z) e3;  z: (X-1,Y-1) e10, (X,Y-1) e11, (X-1,Y) e9, (X,Y) e8.
 template <int E>
 __device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const double* v, int occ_self, int i, int j, int kg,
-                                                    long long slot, unsigned* lo, unsigned* hi, unsigned cell)
+                                                    const McStage& st, unsigned loc, unsigned* lo, unsigned* hi, unsigned cell)
 {
     const McGrid& g = p.g;
     constexpr int I1 = mc_end1(E), I2 = mc_end2(E);
@@ -1179,7 +1204,7 @@ __device__ static inline void mc_create_edge_vertex(const McEmitParams& p, const
         if (E == 11) { mc_gather_from<9>(p, X - 1, Y, Z, nsum); mc_gather_from<8>(p, X, Y, Z, nsum); }
         if (E == 9) { mc_gather_from<8>(p, X, Y, Z, nsum); }
     }
-    mc_store_vertex(p, slot, pos, col, nsum, lo, hi, cell, (unsigned)E);
+    mc_store_vertex(p, st, loc, pos, col, nsum, lo, hi, cell, (unsigned)E);
 }
 
 
@@ -1235,8 +1260,8 @@ __device__ static inline void mc_gather_from_nb(const McEmitParams& p, const dou
 }
 
 template <int E>
-__device__ static inline void mc_create_interior_vertex(const McEmitParams& p, unsigned long long aux, int i, int j, int kg, long long slot,
-                                                        unsigned* lo, unsigned* hi, unsigned cell, const unsigned* s_quick,
+__device__ static inline void mc_create_interior_vertex(const McEmitParams& p, unsigned long long aux, int i, int j, int kg, const McStage& st,
+                                                        unsigned loc, unsigned* lo, unsigned* hi, unsigned cell, const unsigned* s_quick,
                                                         const unsigned long long* s_occ)
 {
     typedef McEdgeGeom<E> G;
@@ -1300,12 +1325,12 @@ __device__ static inline void mc_create_interior_vertex(const McEmitParams& p, u
     mc_gather_from_nb<AXIS, 1, 0, ES1>(p, nb, i + pi, j + pj, kg, s_quick, s_occ, nsum);
     mc_gather_from_nb<AXIS, 0, 1, ES2>(p, nb, i, j + qj, kg + qk, s_quick, s_occ, nsum);
     mc_gather_from_nb<AXIS, 1, 1, ES3>(p, nb, i + pi, j + pj + qj, kg + qk, s_quick, s_occ, nsum);
-    mc_store_vertex(p, slot, pos, col, nsum, lo, hi, cell, (unsigned)E);
+    mc_store_vertex(p, st, loc, pos, col, nsum, lo, hi, cell, (unsigned)E);
 }
 
 // Cell.CalculateCenterVertex (Cell.cs:501-549) + its accumulated gradient
 __device__ static inline void mc_create_center_vertex(const McEmitParams& p, const double* v, int times, int i, int j, int kg,
-                                                      long long slot, unsigned* lo, unsigned* hi, unsigned cell)
+                                                      const McStage& st, unsigned loc, unsigned* lo, unsigned* hi, unsigned cell)
 {
     const McGrid& g = p.g;
     const double stp = (double)g.step;
@@ -1344,7 +1369,7 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
     }
     const float gx = (float)gs[0], gy = (float)gs[1], gz = (float)gs[2];
     for (int t = 0; t < times; t++) { nsum.x = nsum.x + gx; nsum.y = nsum.y + gy; nsum.z = nsum.z + gz; }
-    mc_store_vertex(p, slot, pos, col, nsum, lo, hi, cell, 12u);
+    mc_store_vertex(p, st, loc, pos, col, nsum, lo, hi, cell, 12u);
 }
 
 #define MC_FOR_EDGES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11)
@@ -1357,8 +1382,12 @@ __device__ static inline void mc_create_center_vertex(const McEmitParams& p, con
 //                         inside the per-record kernel the three interior kinds (edges 5, 6, 10) each ran with a third of
 //                         the lanes (12 of 32 lanes active on average, 5.6e8 warp instructions).  Here a block first sorts
 //                         its 1024 tasks by kind in shared memory and then works through one kind at a time with full warps.
+#ifndef MC_VERT_THREADS
 #define MC_VERT_THREADS 256
+#endif
+#ifndef MC_VERT_PER_BLOCK
 #define MC_VERT_PER_BLOCK 1024
+#endif
 
 __global__ void __launch_bounds__(MC_EMIT_THREADS, 12)
 mc_emit_tris_kernel(const McEmitParams p)
@@ -1439,7 +1468,7 @@ mc_emit_tris_kernel(const McEmitParams p)
 
 // creates the vertex of task (record r, slot E) at vertex slot `slot`
 template <int E>
-__device__ static inline void mc_run_vertex_task(const McEmitParams& p, unsigned r, long long slot, unsigned* lo, unsigned* hi)
+__device__ static inline void mc_run_vertex_task(const McEmitParams& p, unsigned r, const McStage& st, unsigned loc, unsigned* lo, unsigned* hi)
 {
     const McGrid& g = p.g;
     const uint4 ra = __ldg(reinterpret_cast<const uint4*>(p.recs + r));      // cell, info, vbase, tbase
@@ -1450,16 +1479,24 @@ __device__ static inline void mc_run_vertex_task(const McEmitParams& p, unsigned
     const int kg = g.k0 + (int)(t2 / (unsigned)g.ncy);
     double v[8];
     mc_load_cell(g, p.dist, i, j, kg, v);
-    if (E == 12) mc_create_center_vertex(p, v, d_meta[MC_LEAF_ROW(ra.y)].occ[12], i, j, kg, slot, lo, hi, ra.x);
-    else mc_create_edge_vertex<(E == 12 ? 0 : E)>(p, v, (int)MC_AUX_OCC(aux, (E == 12 ? 0 : E)), i, j, kg, slot, lo, hi, ra.x);
+    if (E == 12) mc_create_center_vertex(p, v, d_meta[MC_LEAF_ROW(ra.y)].occ[12], i, j, kg, st, loc, lo, hi, ra.x);
+    else mc_create_edge_vertex<(E == 12 ? 0 : E)>(p, v, (int)MC_AUX_OCC(aux, (E == 12 ? 0 : E)), i, j, kg, st, loc, lo, hi, ra.x);
 }
 
+#ifndef MC_VERT_STAGE
+#define MC_VERT_STAGE 0
+#endif
+#define MC_VERT_STAGE_BYTES (MC_VERT_STAGE ? MC_VERT_PER_BLOCK * 9 * 4 : 0)
 #ifndef MC_VERT_MINB
 #define MC_VERT_MINB 4    // measured at 1024^3: 3 (80 regs) 0.683 ms, 4 (64 regs) 0.655 ms, 6 (40 regs) 0.731 ms
 #endif
 __global__ void __launch_bounds__(MC_VERT_THREADS, MC_VERT_MINB)
 mc_emit_verts_kernel(const McEmitParams p)
 {
+#if MC_VERT_STAGE
+    extern __shared__ __align__(16) float s_stage[];
+    const McStage st = {s_stage, s_stage + MC_VERT_PER_BLOCK * 3, s_stage + MC_VERT_PER_BLOCK * 6};
+#endif
     __shared__ uint2 s_item[MC_VERT_PER_BLOCK];      // (record, slot E | local vertex index << 8), grouped by kind
     __shared__ unsigned s_cnt[4], s_base[4];
     __shared__ unsigned s_quick[256];                // cube index -> leaf of an unambiguous cell
@@ -1494,6 +1531,10 @@ mc_emit_verts_kernel(const McEmitParams p)
     __syncthreads();
     // (Measured and dropped: an L2 prefetch pass over all of the block's tasks before the work loops -- 0.39 -> 0.50 ms: the
     // prefetches need the same dependent record load first and then saturate the load/store queue.)
+#if !MC_VERT_STAGE
+    const McStage st = {p.verts + (size_t)first * 3, p.rgb ? p.cols + (size_t)first * 3 : reinterpret_cast<float*>(p.recipes + first),
+                        p.nrms + (size_t)first * 3};
+#endif
     unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
 #define MC_KIND(K, E)                                                                                          \
     for (unsigned idx = tid; idx < s_cnt[K]; idx += MC_VERT_THREADS) {                                         \
@@ -1503,15 +1544,15 @@ mc_emit_verts_kernel(const McEmitParams p)
         const int ci = (int)(ra.x % (unsigned)p.g.ncx);                                                        \
         const unsigned t2 = ra.x / (unsigned)p.g.ncx;                                                          \
         mc_create_interior_vertex<E>(p, aux, ci, (int)(t2 % (unsigned)p.g.ncy), p.g.k0 + (int)(t2 / (unsigned)p.g.ncy), \
-                                     (long long)(first + (it.y >> 8)), lo, hi, ra.x, s_quick, s_occ);          \
+                                     st, it.y >> 8, lo, hi, ra.x, s_quick, s_occ);                             \
     }
     MC_KIND(0, 5) MC_KIND(1, 6) MC_KIND(2, 10)
 #undef MC_KIND
     for (unsigned idx = tid; idx < s_cnt[3]; idx += MC_VERT_THREADS) {
         const uint2 it = s_item[s_base[3] + idx];
-        const long long slot = (long long)(first + (it.y >> 8));
+        const unsigned loc = it.y >> 8;
         switch (it.y & 0xFFu) {
-#define MC_CASE(E) case E: mc_run_vertex_task<E>(p, it.x, slot, lo, hi); break;
+#define MC_CASE(E) case E: mc_run_vertex_task<E>(p, it.x, st, loc, lo, hi); break;
         MC_CASE(0) MC_CASE(1) MC_CASE(2) MC_CASE(3) MC_CASE(4) MC_CASE(7) MC_CASE(8) MC_CASE(9) MC_CASE(11) MC_CASE(12)
 #undef MC_CASE
         default: break;
@@ -1526,6 +1567,30 @@ mc_emit_verts_kernel(const McEmitParams p)
             if (h != 0u) atomicMax(p.aabb_keys + 3 + a, h);
         }
     }
+#if MC_VERT_STAGE
+    // the staged rows leave coalesced: slots [first, first + n) are contiguous in every output array
+    __syncthreads();
+    const unsigned n = min((unsigned)MC_VERT_PER_BLOCK, p.vert_end - first);
+    float* gv = p.verts + (size_t)first * 3;
+    float* gn = p.nrms + (size_t)first * 3;
+    for (unsigned k = tid; k < n * 3u; k += MC_VERT_THREADS) { gv[k] = st.v[k]; gn[k] = st.n[k]; }
+    if (p.rgb) {
+        float* gc = p.cols + (size_t)first * 3;
+        for (unsigned k = tid; k < n * 3u; k += MC_VERT_THREADS) gc[k] = st.c[k];
+    } else {
+        float* gr = reinterpret_cast<float*>(p.recipes + first);
+        for (unsigned k = tid; k < n * 2u; k += MC_VERT_THREADS) gr[k] = st.c[k];
+    }
+#endif
+}
+
+cudaError_t mc_init_kernels()
+{
+#if MC_VERT_STAGE
+    return cudaFuncSetAttribute(mc_emit_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_VERT_STAGE_BYTES);
+#else
+    return cudaSuccess;
+#endif
 }
 
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
@@ -1536,7 +1601,7 @@ cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
     cudaError_t e = cudaGetLastError();
     const unsigned nv = p.vert_end - p.vert_begin;
     if (e != cudaSuccess || nv == 0) return e;
-    mc_emit_verts_kernel<<<(nv + MC_VERT_PER_BLOCK - 1u) / MC_VERT_PER_BLOCK, MC_VERT_THREADS, 0, s>>>(p);
+    mc_emit_verts_kernel<<<(nv + MC_VERT_PER_BLOCK - 1u) / MC_VERT_PER_BLOCK, MC_VERT_THREADS, MC_VERT_STAGE_BYTES, s>>>(p);
     return cudaGetLastError();
 }
 

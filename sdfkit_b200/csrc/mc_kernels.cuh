@@ -83,11 +83,13 @@ cudaError_t mc_launch_classify(const McGrid& g, const float* dist, unsigned* cou
 // same outputs from the sign planes written by the sampling kernels (step == 1): no pass over the distance field
 cudaError_t mc_launch_classify_signs(const McGrid& g, const uint4* signs, unsigned tiles_per_row, unsigned nzg, unsigned* counts,
                                      uint4* masks, cudaStream_t s);
-// base[i] is written only for items with a non-zero count and at multiples of write_every (1 = everywhere)
+// base[i] is written only for items with a non-zero count and at multiples of write_every (1 = everywhere);
+// alist (optional, first scan): alist[rank among the non-empty items] = item, i.e. the list of active chunks
 cudaError_t mc_launch_scan(const unsigned* counts, uint4* base, unsigned nchunks, void* scan_ws, size_t ws_bytes,
-                           McTotals* totals, unsigned write_every, cudaStream_t s);
+                           McTotals* totals, unsigned write_every, unsigned* alist, cudaStream_t s);
 size_t mc_scan_workspace_bytes(unsigned nchunks);
-cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* counts, const uint4* base,
+// visits the nactive active chunks listed in alist (by rank)
+cudaError_t mc_launch_compact(const McGrid& g, const float* dist, const unsigned* alist, unsigned nactive, const uint4* base,
                               McRecord* recs, const uint4* masks, unsigned* acounts, cudaStream_t s);
 cudaError_t mc_launch_boundary(const uint4* base, const uint4* abase, size_t idx, void* dst_host_mapped, cudaStream_t s);
 // the same prefixes at the first chunk of each of nlayers cell layers (per_layer chunks apart): nlayers uint4 to mapped host memory
