@@ -703,9 +703,12 @@ cudaError_t mc_launch_classify_signs(const McGrid& g, const uint4* signs, unsign
 // K3 mc_scan: exclusive prefix sums (records, vertices, triangles) over the chunk counts, in visiting
 // order.  Single pass: warp-shuffle scans inside a tile, decoupled look-back between tiles.
 // ---------------------------------------------------------------------------------------------------
+// (Measured and dropped: 16384-item tiles -- 64 items per thread in four rounds, read twice -- so that the 8.4 M chunks of a
+// 1024^3 grid are 512 tiles in one wave instead of 2048 in two: 0.095 -> 0.125 ms for the two scans.)
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 16
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_ROUNDS 1
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS * SCAN_ROUNDS)
 
 struct ScanWs {
     unsigned ticket;
@@ -741,14 +744,27 @@ mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, un
     __syncthreads();
     const unsigned tile = s_tile;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned first = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const unsigned first = tile * SCAN_TILE + threadIdx.x * (SCAN_ITEMS * SCAN_ROUNDS);   // (n <= 0xFFFFFFF0: no overflow below)
 
     unsigned c[SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) c[k] = (first + k < n) ? counts[first + k] : 0u;
     uint3 sum = make_uint3(0, 0, 0);
+#pragma unroll 1
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        const unsigned f = first + (unsigned)r * SCAN_ITEMS;
+        if (f >= n) break;
+        if (f + SCAN_ITEMS <= n) {                             // (rounds start at multiples of 16 items: 64-byte aligned)
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { sum.x += MC_CNT_ACT(c[k]); sum.y += MC_CNT_V(c[k]); sum.z += MC_CNT_T(c[k]); }
+            for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(counts + f + 4 * q);
+                c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) c[k] = (f + k < n) ? counts[f + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { sum.x += MC_CNT_ACT(c[k]); sum.y += MC_CNT_V(c[k]); sum.z += MC_CNT_T(c[k]); }
+    }
     // inclusive warp scan
     uint3 inc = sum;
 #pragma unroll
@@ -804,14 +820,21 @@ mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, un
     __syncthreads();
     const uint3 te = s_excl;
     uint3 run = make_uint3(te.x + woff.x + inc.x - sum.x, te.y + woff.y + inc.y - sum.y, te.z + woff.z + inc.z - sum.z);
+#pragma unroll 1
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        const unsigned f = first + (unsigned)r * SCAN_ITEMS;
+        if (f >= n) break;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        // prefixes are only ever looked up for non-empty items (the lookups test the count first) and at multiples of
-        // write_every (cell-layer boundaries): 99 % of the 16-byte stores of the first scan are skipped
-        if (first + k < n && (c[k] != 0u || (first + k) % write_every == 0u)) base[first + k] = make_uint4(run.x, run.y, run.z, c[k]);
-        // first scan: the active chunks by rank (run.y counts them), so that K4a visits those only
-        if (alist && first + k < n && c[k] != 0u) alist[run.y] = first + k;
-        run.x += MC_CNT_ACT(c[k]); run.y += MC_CNT_V(c[k]); run.z += MC_CNT_T(c[k]);
+        for (int k = 0; k < SCAN_ITEMS; k++) c[k] = (f + k < n) ? counts[f + k] : 0u;      // second read: L1 / L2
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            // prefixes are only ever looked up for non-empty items (the lookups test the count first) and at multiples of
+            // write_every (cell-layer boundaries): 99 % of the 16-byte stores of the first scan are skipped
+            if (f + k < n && (c[k] != 0u || (f + k) % write_every == 0u)) base[f + k] = make_uint4(run.x, run.y, run.z, c[k]);
+            // first scan: the active chunks by rank (run.y counts them), so that K4a visits those only
+            if (alist && f + k < n && c[k] != 0u) alist[run.y] = f + k;
+            run.x += MC_CNT_ACT(c[k]); run.y += MC_CNT_V(c[k]); run.z += MC_CNT_T(c[k]);
+        }
     }
 }
 
@@ -1425,26 +1448,55 @@ mc_emit_tris_kernel(const McEmitParams p)
             own &= own - 1u;
             vid[e] = (int)(rec.vbase + (unsigned)__popc((unsigned)meta->before[e] & owned));
         }
-        // per edge e: creator offset (di | dj << 1 | dk << 2, each 0 or -1) and which rank field of its record (0: e5, 1: e6, 2: e10)
-        const unsigned long long creator = 0x882530800a2b08eull;
-        unsigned need = refd & ~owned;
-        while (need) {
-            const int e = __ffs((int)need) - 1;
-            need &= need - 1u;
-            const unsigned t = (unsigned)(creator >> (5 * e)) & 31u;
-            const int oi = i - (int)(t & 1u), oj = j - (int)((t >> 1) & 1u), okl = kl - (int)((t >> 2) & 1u);
-            unsigned cvb = 0;
-            const int orr = (okl >= 0) ? mc_find_record(p, oi, oj, okl, &cvb) : -1;
-            int id = 0;
-            if (orr < 0) atomicExch(p.error_flag, 1);
-            else {
-                const McRecord* orp = p.recs + orr;
-                const uint4 oa = __ldg(reinterpret_cast<const uint4*>(orp));          // cell, info, vbase (chunk-local), tbase
-                if (MC_LEAF_NT(oa.y) == 0u) atomicExch(p.error_flag, 5);               // creator is an "impossible case 13" cell
-                else id = (int)(oa.z + cvb + MC_AUX_RANK(__ldg(&orp->aux), t >> 3));
-            }
-            vid[e] = id;
+        // Every other edge is created by one of SIX neighbours (offsets -1 in i / j / k), each answering for up to two edges
+        // with the rank fields of its record (0: e5, 1: e6, 2: e10):
+        //   (0,0,-1): e1 <- its e5, e2 <- its e6     (-1,0,-1): e3 <- e5     (0,-1,-1): e0 <- e6
+        //   (0,-1,0): e4 <- its e6, e9 <- its e10    (-1,-1,0): e8 <- e10    (-1,0,0):  e7 <- e5, e11 <- e10
+        // One look-up per NEIGHBOUR (round 2: one per edge, 9 instead of 6), the chunk words (count, first record, mask) of
+        // neighbours in the same chunk fetched once, and the three chunk words / the three record words requested together
+        // instead of one after the other (4 dependent round trips -> 2).
+        const unsigned need = refd & ~owned;
+        unsigned cchunk = 0xFFFFFFFFu, ccnt = 0u;
+        uint4 cb = make_uint4(0, 0, 0, 0), cm = make_uint4(0, 0, 0, 0);
+#define MC_NEIGHBOUR(DI, DJ, DK, EA, RA, EB, RB)                                                                       \
+        if (need & ((1u << EA) | (EB >= 0 ? (1u << (EB >= 0 ? EB : 0)) : 0u))) {                                         \
+            const int oi = i - DI, oj = j - DJ, okl = kl - DK;                                                           \
+            int id_a = 0, id_b = 0;                                                                                      \
+            if (okl < 0) atomicExch(p.error_flag, 1);                                                                    \
+            else {                                                                                                       \
+                const unsigned chunk = ((unsigned)okl * (unsigned)g.ncy + (unsigned)oj) * (unsigned)g.cpr + ((unsigned)oi >> 7); \
+                if (chunk != cchunk) {                                                                                   \
+                    cchunk = chunk;                                                                                      \
+                    ccnt = __ldg(p.counts + chunk);                /* base / masks hold data only for active chunks: */  \
+                    cb = __ldg(p.base + chunk);                    /* requested together, used only if the count says so */ \
+                    cm = __ldg(p.masks + chunk);                                                                         \
+                }                                                                                                        \
+                const unsigned q = (unsigned)oi & 127u, w = q >> 5, bit = q & 31u;                                       \
+                const unsigned ww = w == 0 ? cm.x : (w == 1 ? cm.y : (w == 2 ? cm.z : cm.w));                            \
+                if (MC_CNT_ACT(ccnt) == 0u || !((ww >> bit) & 1u)) atomicExch(p.error_flag, 1);                          \
+                else {                                                                                                   \
+                    unsigned rank = __popc(ww & ((1u << bit) - 1u));                                                     \
+                    if (w > 0) rank += __popc(cm.x);                                                                     \
+                    if (w > 1) rank += __popc(cm.y);                                                                     \
+                    if (w > 2) rank += __popc(cm.z);                                                                     \
+                    const McRecord* orp = p.recs + (cb.x + rank);                                                        \
+                    const unsigned cvb = __ldg(&p.abase[cb.y].y);                    /* vertex prefix of the chunk */     \
+                    const uint4 oa = __ldg(reinterpret_cast<const uint4*>(orp));     /* cell, info, vbase (chunk-local), tbase */ \
+                    const unsigned long long oaux = __ldg(&orp->aux);                                                    \
+                    if (MC_LEAF_NT(oa.y) == 0u) atomicExch(p.error_flag, 5);         /* creator is an "impossible case 13" cell */ \
+                    else { id_a = (int)(oa.z + cvb + MC_AUX_RANK(oaux, RA)); id_b = (int)(oa.z + cvb + MC_AUX_RANK(oaux, RB)); } \
+                }                                                                                                        \
+            }                                                                                                            \
+            if ((need >> EA) & 1u) vid[EA] = id_a;                                                                       \
+            if (EB >= 0 && ((need >> (EB >= 0 ? EB : 0)) & 1u)) vid[EB >= 0 ? EB : 0] = id_b;                            \
         }
+        MC_NEIGHBOUR(0, 0, 1, 1, 0, 2, 1)
+        MC_NEIGHBOUR(1, 0, 1, 3, 0, -1, 0)
+        MC_NEIGHBOUR(0, 1, 1, 0, 1, -1, 0)
+        MC_NEIGHBOUR(0, 1, 0, 4, 1, 9, 2)
+        MC_NEIGHBOUR(1, 1, 0, 8, 2, -1, 0)
+        MC_NEIGHBOUR(1, 0, 0, 7, 0, 11, 2)
+#undef MC_NEIGHBOUR
     } else {
 #define VID(E) if ((refd >> E) & 1u) vid[E] = mc_vertex_id<E>(p, rec, meta, owned, i, j, kl, kg);
         MC_FOR_EDGES(VID)

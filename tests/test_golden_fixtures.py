@@ -113,3 +113,20 @@ def test_dialect_text_of_the_benchmark_scenes_is_pinned():
         assert low.body == fix[name]["body"], name
         assert low.flops == fix[name]["flops"] and low.node_count == fix[name]["node_count"]
     assert fix["readme"]["flops"] == 23 and fix["csg50"]["flops"] == 205 and fix["csg50"]["node_count"] == 50
+
+
+def test_case13_never_takes_an_impossible_subconfiguration(oracle):
+    """MarchingCubes.cs:364-366: a case-13 cell whose six face tests index one of the 18 `-1` entries of subconfig13 emits
+    nothing in the reference; the GPU formulation (creator = first sharing cell in visiting order) reports SDFK_ERR_INTERNAL
+    if a neighbour needed a vertex from such a cell.  The six tests are functions of the same eight corner
+    values, and Lewiner's table marks exactly the combinations that no eight values can produce: on white noise -- thousands
+    of case-13 cells with every reachable face-test pattern -- the branch is never taken."""
+    rng = np.random.default_rng(13)
+    n13 = nimp = 0
+    for _ in range(2):
+        v = rng.standard_normal((64, 64, 64)).astype(np.float32)
+        m = oracle.marching_cubes(v, np.zeros((64, 64, 64, 3), np.float32), transform=False, debug=True)
+        is13 = (m.cell_index == 165) | (m.cell_index == 90)          # the two checkerboard cube indices = Lewiner case 13
+        n13 += int(is13.sum())
+        nimp += int((is13 & (m.cell_ntris == 0)).sum())
+    assert n13 > 3000 and nimp == 0
