@@ -45,6 +45,7 @@ namespace SdfKit.B200
         [DllImport(Lib)] public static extern int sdfk_mesh_host_ptrs(IntPtr mesh, out float* vertices, out float* colors,
             out float* normals, out int* triangles);
         [DllImport(Lib)] public static extern int sdfk_ctx_set_option(IntPtr ctx, int option, int value);
+        [DllImport(Lib)] public static extern int sdfk_ctx_store_bandwidth(IntPtr ctx, UIntPtr bytes, int reps, out double gbPerS);
         [DllImport(Lib)] public static extern int sdfk_mesh_destroy(IntPtr mesh);
 
         // Not bound here (not needed by the drop-in; see include/sdfk.h): instrumentation (sdfk_ctx_mark / _elapsed / _timer_* /

@@ -93,6 +93,12 @@ int sdfk_ctx_launch_count(sdfk_ctx* ctx, int64_t* launches);
 #define SDFK_OPT_SIGN_PLANES 1
 int sdfk_ctx_set_option(sdfk_ctx* ctx, int option, int value);
 
+/* Measurement aid: the rate (GB/s) at which a store-only kernel -- one CTA per 16 KiB in memory order, the order the sampling
+ * kernels hand their work out in -- fills `bytes` of device memory on device 0 of the context (best of `reps` runs, CUDA events).
+ * The ceiling of Voxels.SampleSdf (SdfKit/Voxels.cs:72-125), which writes 16 B per voxel and reads nothing; a copy (the usual
+ * "HBM bandwidth" figure) is slower than a pure store stream on B200. */
+int sdfk_ctx_store_bandwidth(sdfk_ctx* ctx, size_t bytes, int reps, double* gb_per_s);
+
 /* page-locked host buffers: results exported into them travel at full PCIe speed (a pageable destination is staged
  * by the driver at a fraction of it).  Optional -- every export accepts any host pointer. */
 int sdfk_host_alloc(size_t bytes, void** out);

@@ -33,6 +33,7 @@ SIGNATURES = {
     "sdfk_ctx_elapsed": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     "sdfk_ctx_launch_count": (C.c_int, [_vp, _i64p]),
     "sdfk_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "sdfk_ctx_store_bandwidth": (C.c_int, [_vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "sdfk_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "sdfk_host_free": (C.c_int, [_vp]),
     "sdfk_sdf_compile": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
@@ -257,6 +258,12 @@ class Context:
 
     def set_option(self, option, value):
         check(lib().sdfk_ctx_set_option(self.handle, int(option), int(value)))
+
+    def store_bandwidth(self, nbytes=4 << 30, reps=5):
+        """GB/s of a store-only kernel in memory order (sdfk_ctx_store_bandwidth): the ceiling of the sampling kernels."""
+        g = C.c_double()
+        check(lib().sdfk_ctx_store_bandwidth(self.handle, int(nbytes), int(reps), C.byref(g)))
+        return g.value
 
     def close(self):
         if self.handle:

@@ -63,8 +63,6 @@ __host__ __device__ static inline void mc_edge_corners(int e, int& a, int& b)
     b = B[e];
 }
 
-cudaError_t mc_init_kernels();     // per-device kernel attributes (below)
-
 cudaError_t mc_init_tables()
 {
     static unsigned leaf[256];
@@ -117,7 +115,6 @@ cudaError_t mc_init_tables()
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_cross, cross, sizeof(cross));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_meta, meta, sizeof(meta));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(d_quick, quick, sizeof(quick));
-    if (err == cudaSuccess) err = mc_init_kernels();
     return err;
 }
 
@@ -824,8 +821,10 @@ mc_scan_kernel(const unsigned* __restrict__ counts, uint4* __restrict__ base, un
     for (int r = 0; r < SCAN_ROUNDS; r++) {
         const unsigned f = first + (unsigned)r * SCAN_ITEMS;
         if (f >= n) break;
+        if (SCAN_ROUNDS > 1) {
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) c[k] = (f + k < n) ? counts[f + k] : 0u;      // second read: L1 / L2
+            for (int k = 0; k < SCAN_ITEMS; k++) c[k] = (f + k < n) ? counts[f + k] : 0u;      // second read: L1 / L2
+        }
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) {
             // prefixes are only ever looked up for non-empty items (the lookups test the count first) and at multiples of
@@ -1072,8 +1071,7 @@ __device__ static inline unsigned mc_float_key(float f)   // monotonic float -> 
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// where a block's vertices go, indexed by the local vertex index: rows staged in shared memory (MC_VERT_STAGE) or the output
-// arrays themselves at the block's first slot
+// where a block's vertices go: the output arrays at the block's first slot, indexed by the local vertex index
 struct McStage {
     float* v;      // positions, 3 floats per local vertex
     float* c;      // colours (3 floats) -- or, for distance-only voxels, the (cell, edge) recipe (2 words)
@@ -1097,9 +1095,6 @@ __device__ static inline void mc_store_vertex(const McEmitParams& p, const McSta
         pos = tp;
         n.x = tn.x / l2; n.y = tn.y / l2; n.z = tn.z / l2;
     }
-#ifdef MC_VERT_DIAG_NOSTORE   /* diagnostic build only: how much of the kernel is its stores (results are wrong) */
-    if (pos.x != 123456.789f) return;
-#endif
     float* vo = st.v + loc * 3u;
     float* no = st.n + loc * 3u;
     vo[0] = pos.x; vo[1] = pos.y; vo[2] = pos.z;
@@ -1535,20 +1530,12 @@ __device__ static inline void mc_run_vertex_task(const McEmitParams& p, unsigned
     else mc_create_edge_vertex<(E == 12 ? 0 : E)>(p, v, (int)MC_AUX_OCC(aux, (E == 12 ? 0 : E)), i, j, kg, st, loc, lo, hi, ra.x);
 }
 
-#ifndef MC_VERT_STAGE
-#define MC_VERT_STAGE 0
-#endif
-#define MC_VERT_STAGE_BYTES (MC_VERT_STAGE ? MC_VERT_PER_BLOCK * 9 * 4 : 0)
 #ifndef MC_VERT_MINB
 #define MC_VERT_MINB 4    // measured at 1024^3: 3 (80 regs) 0.683 ms, 4 (64 regs) 0.655 ms, 6 (40 regs) 0.731 ms
 #endif
 __global__ void __launch_bounds__(MC_VERT_THREADS, MC_VERT_MINB)
 mc_emit_verts_kernel(const McEmitParams p)
 {
-#if MC_VERT_STAGE
-    extern __shared__ __align__(16) float s_stage[];
-    const McStage st = {s_stage, s_stage + MC_VERT_PER_BLOCK * 3, s_stage + MC_VERT_PER_BLOCK * 6};
-#endif
     __shared__ uint2 s_item[MC_VERT_PER_BLOCK];      // (record, slot E | local vertex index << 8), grouped by kind
     __shared__ unsigned s_cnt[4], s_base[4];
     __shared__ unsigned s_quick[256];                // cube index -> leaf of an unambiguous cell
@@ -1582,11 +1569,17 @@ mc_emit_verts_kernel(const McEmitParams p)
         if (kind[q] < 4u) s_item[s_base[kind[q]] + pos[q]] = task[q];
     __syncthreads();
     // (Measured and dropped: an L2 prefetch pass over all of the block's tasks before the work loops -- 0.39 -> 0.50 ms: the
-    // prefetches need the same dependent record load first and then saturate the load/store queue.)
-#if !MC_VERT_STAGE
+    // prefetches need the same dependent record load first and then saturate the load/store queue.  Round 2, second session,
+    // all bit-exact and all slower than this kernel's 0.39 ms at 1024^3: the rows of the 3 x 3 x 2
+    // neighbourhood / the two corners' colours as aligned 16-byte loads + selects (0.51 ms at 80 registers; divergent
+    // LDG.128 cost more than three LDG.32 -- the same change made K4a 50 % slower); a block's rows staged in shared memory
+    // and stored coalesced (0.39 ms at 3 CTAs / SM, 0.69 ms at 4: the stage takes the L1 the gathers live on; the scattered
+    // stores themselves are 0.06 ms of the kernel); one launch per kind of vertex so that the hot code fits the 32 KB
+    // instruction cache (3 x 0.32 ms: every launch re-reads the block's sectors and writes partial sectors of the outputs);
+    // fewer vertices in flight for L2 reuse across layers (256..512 per block: 0.48..0.55 ms).  The kernel moves 0.84 GB
+    // from DRAM for a 0.16 GB footprint of touched sectors and runs at the ~3 TB/s this box sustains for scattered sectors.)
     const McStage st = {p.verts + (size_t)first * 3, p.rgb ? p.cols + (size_t)first * 3 : reinterpret_cast<float*>(p.recipes + first),
                         p.nrms + (size_t)first * 3};
-#endif
     unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
 #define MC_KIND(K, E)                                                                                          \
     for (unsigned idx = tid; idx < s_cnt[K]; idx += MC_VERT_THREADS) {                                         \
@@ -1619,30 +1612,6 @@ mc_emit_verts_kernel(const McEmitParams p)
             if (h != 0u) atomicMax(p.aabb_keys + 3 + a, h);
         }
     }
-#if MC_VERT_STAGE
-    // the staged rows leave coalesced: slots [first, first + n) are contiguous in every output array
-    __syncthreads();
-    const unsigned n = min((unsigned)MC_VERT_PER_BLOCK, p.vert_end - first);
-    float* gv = p.verts + (size_t)first * 3;
-    float* gn = p.nrms + (size_t)first * 3;
-    for (unsigned k = tid; k < n * 3u; k += MC_VERT_THREADS) { gv[k] = st.v[k]; gn[k] = st.n[k]; }
-    if (p.rgb) {
-        float* gc = p.cols + (size_t)first * 3;
-        for (unsigned k = tid; k < n * 3u; k += MC_VERT_THREADS) gc[k] = st.c[k];
-    } else {
-        float* gr = reinterpret_cast<float*>(p.recipes + first);
-        for (unsigned k = tid; k < n * 2u; k += MC_VERT_THREADS) gr[k] = st.c[k];
-    }
-#endif
-}
-
-cudaError_t mc_init_kernels()
-{
-#if MC_VERT_STAGE
-    return cudaFuncSetAttribute(mc_emit_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MC_VERT_STAGE_BYTES);
-#else
-    return cudaSuccess;
-#endif
 }
 
 cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
@@ -1653,7 +1622,7 @@ cudaError_t mc_launch_emit(const McEmitParams& p, cudaStream_t s)
     cudaError_t e = cudaGetLastError();
     const unsigned nv = p.vert_end - p.vert_begin;
     if (e != cudaSuccess || nv == 0) return e;
-    mc_emit_verts_kernel<<<(nv + MC_VERT_PER_BLOCK - 1u) / MC_VERT_PER_BLOCK, MC_VERT_THREADS, MC_VERT_STAGE_BYTES, s>>>(p);
+    mc_emit_verts_kernel<<<(nv + MC_VERT_PER_BLOCK - 1u) / MC_VERT_PER_BLOCK, MC_VERT_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

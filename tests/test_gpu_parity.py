@@ -717,3 +717,14 @@ def test_host_mesh_transform_equals_the_fused_device_transform(sk):
     assert_bits_equal(index_space.Max, world.Max, "aabb max")
     f = expr.ToSdfFunc()                                            # SdfExprEx.ToSdfFunc: one point at a time
     assert f((0.1, 0.2, 0.3)).shape == (4,)
+
+
+def test_store_bandwidth_probe(sk):
+    """sdfk_ctx_store_bandwidth (bench.py's `write_only_peak`): a plausible HBM rate, and loud on bad arguments."""
+    from sdfkit_b200 import _native as N
+    ctx = sk.Context(0)
+    g = ctx.store_bandwidth(1 << 30, 2)
+    assert 500.0 < g < 20000.0
+    with pytest.raises(N.SdfkError):
+        ctx.store_bandwidth(1024, 1)            # less than one 16 KiB chunk
+    ctx.close()

@@ -24,11 +24,12 @@ for r in rows[1:]:
         tot[r[ik][:48]] += v; cnt[r[ik][:48]] += 1
 s = sum(tot.values())
 print("# ncu --metrics gpu__time_duration.sum --clock-control none: bench.py --steps 2 --warmup 1 (3 warm-up + 2 timed steps; cold-cache, serialised launches: shares, not absolutes)")
-setup = {k: v for k, v in tot.items() if "constdiv_verify" in k or "selftest" in k}
+setup = {k: v for k, v in tot.items() if "constdiv_verify" in k or "selftest" in k or "store_probe" in k}
 s -= sum(setup.values())
 for k, v in tot.most_common():
     if k in setup:
-        print("%-50s %4d launches  %10.3f ms total  (at ToSdf() time: exhaustive check of a constant division, not part of a step)" % (k, cnt[k], v / 1e6))
+        why = "after the steps: the store-only bandwidth probe behind roofline.write_only_peak" if "store_probe" in k else "at ToSdf() time: exhaustive check of a constant division, not part of a step"
+        print("%-50s %4d launches  %10.3f ms total  (%s)" % (k, cnt[k], v / 1e6, why))
     else:
         print("%-50s %4d launches  %10.3f ms total  %5.1f %% of the steps" % (k, cnt[k], v / 1e6, 100 * v / s))
 PY
