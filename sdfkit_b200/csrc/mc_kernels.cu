@@ -631,6 +631,22 @@ mc_classify_signs_kernel(const McGrid g, const uint4* __restrict__ signs, unsign
             an[0] = c0.x; an[1] = c0.y; an[2] = c0.z; an[3] = c0.w; an[4] = c1.x; an[5] = c1.y; an[6] = c1.z; an[7] = c1.w;
             bn[0] = d0.x; bn[1] = d0.y; bn[2] = d0.z; bn[3] = d0.w; bn[4] = d1.x; bn[5] = d1.y; bn[6] = d1.z; bn[7] = d1.w;
         }
+        // An item whose words are all 0 or all 1 in every lane -- both rows, the next tile's first lane, the first plane of the
+        // next group -- has no sign change: nothing to count (`counts` is zeroed before the launch).  Most items of a scene are
+        // like that (0.4 % of the README scene's cells are active), and this test replaces ~250 instructions by ~30.
+        {
+            unsigned o = 0u, n = 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < MC_SZB; q++) { o |= a[q] | b[q]; n &= a[q] & b[q]; }
+            const unsigned t8 = a[MC_SZB] | b[MC_SZB], u8 = a[MC_SZB] & b[MC_SZB];      // next group: only its first plane (low nibble bits)
+            o |= t8 & 0x0000000Fu; n &= u8 | 0xFFFFFFF0u;
+            if (edge) {
+#pragma unroll
+                for (int q = 0; q < MC_SZB; q++) { o |= (an[q] | bn[q]) & 0x11111111u; n &= (an[q] & bn[q]) | 0xEEEEEEEEu; }   // voxel k = 0 of the next tile
+                o |= (an[MC_SZB] | bn[MC_SZB]) & 1u; n &= (an[MC_SZB] & bn[MC_SZB]) | 0xFFFFFFFEu;
+            }
+            if (__all_sync(FULL, o == 0u) || __all_sync(FULL, n == 0xFFFFFFFFu)) continue;
+        }
         unsigned any[MC_SZB + 1], all[MC_SZB + 1];                        // OR / AND over rows j, j+1 and voxels c, c+1; bit 4p + k
 #pragma unroll
         for (int q = 0; q <= MC_SZB; q++) {
