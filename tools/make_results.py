@@ -31,12 +31,13 @@ w("# RESULTS -- round 2 (measured on boxes of the pool, NVIDIA B200, SM clock %s
     d["clocks"]["sm_mhz"], d["clocks"]["reasons"] or "none"))
 w("All GPU numbers: CUDA events on the library's stream after >= 5 warm-ups (wall clock where a call returns a host result); parity mode\n"
   "(IEEE f32/f64, no FMA contraction), every output bit-exact against the CPU oracle and the committed golden fixtures in the GPU\n"
-  "test-suite (177 tests on one GPU, 178 with two). CPU numbers: the C++ restatement of the reference's CPU path (`oracle/`, g++ -O2\n"
+  "test-suite (178 tests on one GPU, 179 with two). CPU numbers: the C++ restatement of the reference's CPU path (`oracle/`, g++ -O2\n"
   "-ffp-contract=off) on the box's %d host cores, on a bounded sample of the same workload -- the .NET reference itself cannot run here.\n"
   "Raw lines and ncu summaries: `profiles/%s_*` (`profiles/CHANGELOG.md`). Roofline denominators: HBM %.0f GB/s (measured copy,\n"
-  "`MEASURED_PEAKS.json`; a pure store stream can exceed a copy's read+write rate, hence fractions slightly above 1); FP32 without FMA\n"
+  "`MEASURED_PEAKS.json`; a pure store stream exceeds a copy's read+write rate on this part -- %.0f GB/s, measured by `bench.py` in the same run with\n"
+  "the library's store-only probe -- hence K1's fraction above 1); FP32 without FMA\n"
   "%.3g lane-op/s (measured FMUL+FADD chains, `profiles/fp32_peak.json`). Regenerate: `python tools/make_results.py %s`.\n" % (
-      cpu["cores"], tag, d["roofline"]["peak"], c3["roofline"]["peak"] * 1e12, tag))
+      cpu["cores"], tag, d["roofline"]["peak"], d["roofline"].get("write_only_peak") or float("nan"), c3["roofline"]["peak"] * 1e12, tag))
 w("## bench.py (README RepeatXY scene -> Voxels (clip) -> MarchingCubes; one step = sample 16 B/voxel + mesh)\n")
 w("Weak scaling, one process per GPU under torchrun, NCCL count all-gather (what the driver runs):\n")
 w("| GPUs | grid | ms/step | voxels/s (whole job) | tris/s | K1 fraction of HBM peak | fused `Sdf.ToMesh` step (device) | e2e `Sdf.ToMesh`, mesh in host memory (mean / median) | parity_check |")
@@ -80,11 +81,20 @@ w("Stage times at 1024^3 on one GPU (ms): K1 sample %.2f | K2' classify (sign bl
 rm = d["roofline_mesh"]
 w("| kernel | algorithmic bytes / flops | time | achieved | fraction of roofline | round 1 |")
 w("|---|---|---|---|---|---|")
-w("| K1 `sdfk_k_sample` (README) | 16 B x 1.07e9 voxels = 17.18 GB written (ncu: 17.17 GB DRAM writes, 0.4 MB reads) | %.2f ms | %.0f GB/s | **%.2f** of HBM | 2.70 ms, 0.97 |" % (
-    st["sample_ms"], d["roofline"]["achieved"], d["roofline"]["frac"]))
+tj = load(tag + "_k1_traffic.json") or {}
+w("| K1 `sdfk_k_sample` (README) | 16 B x 1.07e9 voxels = 17.18 GB written (ncu: %.2f GB DRAM writes incl. 0.13 GB of sign blocks, %.1f MB reads) | %.2f ms | %.0f GB/s | **%.2f** of the HBM copy peak, %.2f of the store-only rate | 2.70 ms, 0.97 |" % (
+    tj.get("dram_bytes_write", float("nan")) / 1e9, tj.get("dram_bytes_read", float("nan")) / 1e6,
+    st["sample_ms"], d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline"].get("frac_of_write_only_peak") or float("nan")))
 w("| K1 `sdfk_k_sample` (CSG-50, config 3) | 205 IEEE f32 ops x 1.07e9 voxels | %.2f ms | %.1f Top/s | **%.2f** of the no-FMA FP32 rate (%.2f of HBM) | 10.82 ms, 0.58 |" % (
     c3["sample_ms"], c3["roofline"]["achieved"], c3["roofline"]["frac"], c3["roofline"]["hbm_frac"]))
-w("| K1d `sdfk_k_sample_dist8` | 4 B x 1.07e9 = 4.29 GB written | 0.684 ms | 6.28 TB/s | **0.96** of HBM | 0.81 ms, 0.81 |")
+k1d = float("nan")
+try:
+    for ln in open(os.path.join(P, tag + "_kernels.txt")):
+        if " readme " in ln and "K1d" in ln:
+            k1d = float(ln.split("K1d")[1].split("ms")[0])
+except OSError:
+    pass
+w("| K1d `sdfk_k_sample_dist8` | 4 B x 1.07e9 = 4.29 GB written | %.3f ms | %.2f TB/s | **%.2f** of HBM | 0.81 ms, 0.81 |" % (k1d, 4.294967296 / k1d, 4294.967296 / k1d / d["roofline"]["peak"]))
 w("| K2'-K4b meshing (sum) | SURVEY 8(d): %.2f GB; sign-block formulation: %.2f GB | %.2f ms | %.3g tris/s, %.3g cells/s | %.2f of HBM by 8(d)'s bytes, %.2f by the bytes really needed (latency-bound gathers over 0.4 %% of the cells) | 1.02 ms |" % (
     rm["algorithmic_bytes_8d"] / 1e9, rm["algorithmic_bytes_sign_blocks"] / 1e9, rm["ms"], rm["tris_per_s"], rm["cells_per_s"], rm["frac_8d"], rm["frac_sign_blocks"]))
 k5 = c5["readme"]
@@ -120,12 +130,25 @@ if r1:
     w("| e2e `Sdf.ToMesh` 1024^3 (mean over the timed steps) | %.2f ms (driver: 8.78 mean / 6.02 median) | %.2f ms (max %.2f) |" % (
         r1["e2e"]["ms_per_step"], d["e2e"]["ms_per_step"], d["e2e"]["ms_per_step_max"]))
 w("| CSG-50 sampling 1024^3 | 10.82 ms (0.58 of FP32) | %.2f ms (%.2f) |" % (c3["sample_ms"], c3["roofline"]["frac"]))
-w("| K1d distance-only sampling | 0.81 ms | 0.684 ms |")
+w("| K1d distance-only sampling | 0.81 ms | %.3f ms |" % k1d)
 w("| `ToImage` 1080p kernel (README) | 0.189 ms | %.3f ms |" % k5["kernel_ms"])
 w("| `mc_emit_verts` | 0.44 ms | 0.39 ms |")
 w("| 1024^3 on 8 GPUs (strong) | not available | %.2f ms device step, %.2f ms e2e |" % (S["by_devices"].get("8", {}).get("device_step_wall_ms", float("nan")), S["by_devices"].get("8", {}).get("e2e_ms", float("nan"))))
 w("| weak scaling 1 -> 8 GPUs | 7.6x (N=4 efficiency 0.88) | %.2fx |" % ((B[8]["value"] / d["value"]) if B[8] else float("nan")))
 w("| reference arm | 384^3 labelled as 1024^3 | 512^3, labelled as measured, `same_config: false` |")
+w("\n## Second session of round 2 against the first (what `profiles/r02_*` held before: commit 56abbbc)\n")
+w("| | first session | second session | what changed |")
+w("|---|---|---|---|")
+w("| K1 `sdfk_k_sample` 1024^3 README | 2.62 ms = 6.56 TB/s | %.2f ms = %.2f TB/s | work items = 32-slice column segments handed out in memory order (DESIGN.md section 4, `tools/micro/store_*.cu`) |" % (st["sample_ms"], d["roofline"]["achieved"] / 1e3))
+w("| 1-GPU step 1024^3 | 3.73 ms = 2.88e11 voxels/s | %.2f ms = %.3g voxels/s | K1, K4a, K3, K2' below |" % (d["ms_per_step"], d["value"]))
+w("| K2' classify / K3 scans / K4a compact | 0.14 / 0.09 / 0.20 ms | %.2f / %.3f / %.2f ms | items without a sign change skipped; 16-byte count loads; active-chunk list |" % (st["classify_ms"], st["scan_ms"], st["compact_ms"]))
+w("| fused `Sdf.ToMesh` step (device) | 1.77 ms | %.2f ms | K1d in 128-slice segments in order + the meshing changes |" % d["fused_to_mesh"]["ms_per_step"])
+w("| e2e `Sdf.ToMesh` 1024^3 | 5.46 ms (box A) | %.2f ms (this box; interleaved A/B on one box: 5.38 -> 5.17 ms) | slab cuts follow the surface, sub-ranges double, meshing stream at high priority |" % d["e2e"]["ms_per_step"])
+w("| CSG-50: sampling / e2e `Sdf.ToMesh` | 8.74 / 9.25 ms | %.2f / %.2f ms | the same |" % (c3["sample_ms"], c3["e2e"]["ms_per_step"]))
+w("| `ToImage` 1080p through the API (README / Perf scene) | 0.72 / 0.87 ms | %.2f / %.2f ms | row bands rendered while the previous band crosses PCIe |" % (c5["readme"]["ms_per_image"], c5["perf_program"]["ms_per_image"]))
+if B[8]:
+    w("| 8 GPUs: weak step 2048^3 / strong device step 1024^3 | 3.66 ms = 2.35e12 voxels/s / 0.78 ms | %.2f ms = %.3g voxels/s / %.2f ms | the same kernels |" % (
+        B[8]["ms_per_step"], B[8]["value"], S["by_devices"].get("8", {}).get("device_step_wall_ms", float("nan"))))
 w("\nParity unpinned by the reference's own tests (vertex positions / normals / colours, triangle order, the ambiguous Lewiner\n"
   "branches, colour renders): the oracle restatement is the only authority there (DESIGN.md section 6); GPU and oracle agree bit for bit\n"
   "on white noise (all 14 cases incl. centre vertices) and on every scene above.\n")
