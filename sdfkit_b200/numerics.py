@@ -73,9 +73,25 @@ def create_scale(x, y, z):
     return m
 
 
+_LOOK_AT_MEMO = {}
+
+
 def create_look_at(camera_position, camera_target, camera_up):
-    """Matrix4x4.CreateLookAt (right-handed)."""
+    """Matrix4x4.CreateLookAt (right-handed).  Memoised on the float32 bits of its nine inputs: the numpy float32 emulation
+    costs ~50 us, a tenth of a 1080p Sdf.ToImage call."""
     pos, tgt, up = vec3(camera_position), vec3(camera_target), vec3(camera_up)
+    key = pos.tobytes() + tgt.tobytes() + up.tobytes()
+    hit = _LOOK_AT_MEMO.get(key)
+    if hit is not None:
+        return hit.copy()
+    m = _create_look_at(pos, tgt, up)
+    if len(_LOOK_AT_MEMO) >= 64:
+        _LOOK_AT_MEMO.clear()
+    _LOOK_AT_MEMO[key] = m.copy()
+    return m
+
+
+def _create_look_at(pos, tgt, up):
     zaxis = normalize3((pos - tgt).astype(np.float32))
     xaxis = normalize3(cross3(up, zaxis))
     yaxis = cross3(zaxis, xaxis)
