@@ -1294,7 +1294,7 @@ __device__ static inline void mc_gather_from_nb(const McEmitParams& p, const dou
 }
 
 template <int E>
-__device__ static inline void mc_create_interior_vertex(const McEmitParams& p, unsigned long long aux, int i, int j, int kg, const McStage& st,
+__device__ static inline void mc_create_interior_vertex(const McEmitParams& p, int occ_self, int i, int j, int kg, const McStage& st,
                                                         unsigned loc, unsigned* lo, unsigned* hi, unsigned cell, const unsigned* s_quick,
                                                         const unsigned long long* s_occ)
 {
@@ -1351,7 +1351,7 @@ __device__ static inline void mc_create_interior_vertex(const McEmitParams& p, u
         col.x = (float)(cm.x / ff); col.y = (float)(cm.y / ff); col.z = (float)(cm.z / ff);
     }
     // normals: the creating cell first, then the other sharing cells in visiting order
-    mc_add_edge_gradients<E>(v, (int)MC_AUX_OCC(aux, E), nsum);
+    mc_add_edge_gradients<E>(v, occ_self, nsum);
     constexpr int ES1 = AXIS == 0 ? 4 : (AXIS == 1 ? 7 : 11), ES2 = AXIS == 0 ? 2 : (AXIS == 1 ? 1 : 9), ES3 = AXIS == 0 ? 0 : (AXIS == 1 ? 3 : 8);
     // cell (P, Q): +P in the lower perpendicular axis, +Q in the higher one
     const int pi = AXIS == 0 ? 0 : 1, pj = AXIS == 0 ? 1 : 0;                    // what +P adds to (ci, cj)
@@ -1525,7 +1525,10 @@ mc_emit_tris_kernel(const McEmitParams p)
     while (mine) {
         const int e = __ffs((int)mine) - 1;
         mine &= mine - 1u;
-        p.tasks[(long long)vid[e] - (long long)p.vlocal0] = make_uint2(r, (unsigned)e);
+        // edges 5, 6, 10 (what mc_emit_verts creates from the voxel neighbourhood alone): the task carries the CELL and how often
+        // the cell's own row references the edge, so that the vertex kernel starts its gathers without waiting for the record
+        const bool nb = e == 5 || e == 6 || e == 10;
+        p.tasks[(long long)vid[e] - (long long)p.vlocal0] = nb ? make_uint2(rec.cell, (unsigned)e | ((unsigned)meta->occ[e] << 4)) : make_uint2(r, (unsigned)e);
     }
 }
 
@@ -1571,9 +1574,9 @@ mc_emit_verts_kernel(const McEmitParams p)
         kind[q] = 4u;
         if (vtx < p.vert_end) {
             task[q] = __ldg(p.tasks + vtx);
-            const unsigned e = task[q].y;
+            const unsigned e = task[q].y & 15u;
             kind[q] = e == 5u ? 0u : (e == 6u ? 1u : (e == 10u ? 2u : 3u));
-            task[q].y = e | (loc << 8);
+            task[q].y = (task[q].y & 0xFFu) | (loc << 8);         // slot E [0:4) | own occurrence count [4:8) | local vertex index
             pos[q] = atomicAdd(&s_cnt[kind[q]], 1u);
         }
     }
@@ -1592,27 +1595,28 @@ mc_emit_verts_kernel(const McEmitParams p)
     // and stored coalesced (0.39 ms at 3 CTAs / SM, 0.69 ms at 4: the stage takes the L1 the gathers live on; the scattered
     // stores themselves are 0.06 ms of the kernel); one launch per kind of vertex so that the hot code fits the 32 KB
     // instruction cache (3 x 0.32 ms: every launch re-reads the block's sectors and writes partial sectors of the outputs);
-    // fewer vertices in flight for L2 reuse across layers (256..512 per block: 0.48..0.55 ms).  The kernel moves 0.84 GB
+    // fewer vertices in flight for L2 reuse across layers (256..512 per block: 0.48..0.55 ms); the sharing cells' corners from
+    // dense 32-byte "corner blocks" that K4a wrote next to the records instead of the voxel gathers (0.39 -> 0.46 ms, K4a
+    // +0.025 ms: one more dependent look-up per vertex outweighs 14 fewer scattered loads -- the kernel is bound by the
+    // LATENCY of its dependent loads at 32 resident warps, which is why the tasks now carry the cell id).  The kernel moves 0.84 GB
     // from DRAM for a 0.16 GB footprint of touched sectors and runs at the ~3 TB/s this box sustains for scattered sectors.)
     const McStage st = {p.verts + (size_t)first * 3, p.rgb ? p.cols + (size_t)first * 3 : reinterpret_cast<float*>(p.recipes + first),
                         p.nrms + (size_t)first * 3};
     unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
 #define MC_KIND(K, E)                                                                                          \
     for (unsigned idx = tid; idx < s_cnt[K]; idx += MC_VERT_THREADS) {                                         \
-        const uint2 it = s_item[s_base[K] + idx];                                                              \
-        const uint4 ra = __ldg(reinterpret_cast<const uint4*>(p.recs + it.x));      /* cell, info, vbase, tbase */ \
-        const unsigned long long aux = __ldg(&p.recs[it.x].aux);                                               \
-        const int ci = (int)(ra.x % (unsigned)p.g.ncx);                                                        \
-        const unsigned t2 = ra.x / (unsigned)p.g.ncx;                                                          \
-        mc_create_interior_vertex<E>(p, aux, ci, (int)(t2 % (unsigned)p.g.ncy), p.g.k0 + (int)(t2 / (unsigned)p.g.ncy), \
-                                     st, it.y >> 8, lo, hi, ra.x, s_quick, s_occ);                             \
+        const uint2 it = s_item[s_base[K] + idx];                     /* cell, E | own occurrences << 4 | local index << 8 */ \
+        const int ci = (int)(it.x % (unsigned)p.g.ncx);                                                        \
+        const unsigned t2 = it.x / (unsigned)p.g.ncx;                                                          \
+        mc_create_interior_vertex<E>(p, (int)((it.y >> 4) & 15u), ci, (int)(t2 % (unsigned)p.g.ncy), p.g.k0 + (int)(t2 / (unsigned)p.g.ncy), \
+                                     st, it.y >> 8, lo, hi, it.x, s_quick, s_occ);                             \
     }
     MC_KIND(0, 5) MC_KIND(1, 6) MC_KIND(2, 10)
 #undef MC_KIND
     for (unsigned idx = tid; idx < s_cnt[3]; idx += MC_VERT_THREADS) {
         const uint2 it = s_item[s_base[3] + idx];
         const unsigned loc = it.y >> 8;
-        switch (it.y & 0xFFu) {
+        switch (it.y & 15u) {
 #define MC_CASE(E) case E: mc_run_vertex_task<E>(p, it.x, st, loc, lo, hi); break;
         MC_CASE(0) MC_CASE(1) MC_CASE(2) MC_CASE(3) MC_CASE(4) MC_CASE(7) MC_CASE(8) MC_CASE(9) MC_CASE(11) MC_CASE(12)
 #undef MC_CASE

@@ -64,7 +64,8 @@ struct McEmitParams {
     float* nrms;
     int* tris;
     uint2* recipes;                // distance-only voxels (rgb == NULL): per vertex (cell, edge) for the deferred colours
-    uint2* tasks;                  // per vertex slot: (record, slot E) of the cell that creates it (tris kernel -> verts kernel)
+    uint2* tasks;                  // per vertex slot, tris kernel -> verts kernel: (record, slot E) of the cell that creates it; for
+                                   // slots 5, 6, 10: (cell id, E | the cell's own reference count of the edge << 4)
     unsigned vert_begin, vert_end; // slab-local vertex slots created by records [rec_begin, rec_end)
     unsigned* aabb_keys;           // 6 ordered-uint keys: min xyz, max xyz
     int has_xf;
