@@ -15,6 +15,18 @@ def load(name):
     return json.load(open(path)) if os.path.exists(path) else None
 
 
+def ncu_ms(name):
+    """gpu__time_duration of the one launch summarised in profiles/<tag>_ncu_<name>.txt (ms; cold-cache under ncu)"""
+    try:
+        for ln in open(os.path.join(P, "%s_ncu_%s.txt" % (tag, name))):
+            if "gpu__time_duration.sum" in ln:
+                v, unit = ln.split()[1:3]
+                return float(v) * {"us": 1e-3, "ms": 1.0, "ns": 1e-6}.get(unit, 1.0)
+    except OSError:
+        pass
+    return float("nan")
+
+
 B = {n: load("%s_bench_%dgpu.json" % (tag, n)) for n in (1, 2, 4, 8)}
 ref = load(tag + "_bench_reference.json")
 r1 = load("r01s6_bench_1gpu.json")
@@ -75,9 +87,9 @@ w("\nCPU restatement on a %d^3 sample (%d cores sampling, 1 thread meshing, like
   "prints the grid it measured (%s, warm-up %d, %d steps) and `same_config: false`.\n" % (
       cpu["detail"]["grid"][0], cpu["cores"], cpu["value"], cpu["detail"]["sample_voxels_per_s"], cpu["detail"]["mesh_tris_per_s"],
       d["value"] / cpu["value"], d["e2e"]["value"] / cpu["value"], "x".join(str(g) for g in ref["config"]["grid"]), ref["warmup"], ref["steps"]))
-w("Stage times at 1024^3 on one GPU (ms): K1 sample %.2f | K2' classify (sign blocks) %.2f | K3 scans %.2f | K4a compact %.2f | K4b emit %.2f (triangles 0.15 + vertices 0.39).\n"
+w("Stage times at 1024^3 on one GPU (ms): K1 sample %.2f | K2' classify (sign blocks) %.2f | K3 scans %.2f | K4a compact %.2f | K4b emit %.2f (under ncu: triangles %.2f + vertices %.2f).\n"
   "ncu launch list of the same command: `profiles/%s_launches_step_summary.txt` (the same shares as the event-timed stages).\n" % (
-      st["sample_ms"], st["classify_ms"], st["scan_ms"], st["compact_ms"], st["emit_ms"], tag))
+      st["sample_ms"], st["classify_ms"], st["scan_ms"], st["compact_ms"], st["emit_ms"], ncu_ms("k4b_emit_tris"), ncu_ms("k4b_emit_verts"), tag))
 rm = d["roofline_mesh"]
 w("| kernel | algorithmic bytes / flops | time | achieved | fraction of roofline | round 1 |")
 w("|---|---|---|---|---|---|")
@@ -132,7 +144,7 @@ if r1:
 w("| CSG-50 sampling 1024^3 | 10.82 ms (0.58 of FP32) | %.2f ms (%.2f) |" % (c3["sample_ms"], c3["roofline"]["frac"]))
 w("| K1d distance-only sampling | 0.81 ms | %.3f ms |" % k1d)
 w("| `ToImage` 1080p kernel (README) | 0.189 ms | %.3f ms |" % k5["kernel_ms"])
-w("| `mc_emit_verts` | 0.44 ms | 0.39 ms |")
+w("| `mc_emit_verts` (one launch under ncu) | 0.44 ms | %.2f ms |" % ncu_ms("k4b_emit_verts"))
 w("| 1024^3 on 8 GPUs (strong) | not available | %.2f ms device step, %.2f ms e2e |" % (S["by_devices"].get("8", {}).get("device_step_wall_ms", float("nan")), S["by_devices"].get("8", {}).get("e2e_ms", float("nan"))))
 w("| weak scaling 1 -> 8 GPUs | 7.6x (N=4 efficiency 0.88) | %.2fx |" % ((B[8]["value"] / d["value"]) if B[8] else float("nan")))
 w("| reference arm | 384^3 labelled as 1024^3 | 512^3, labelled as measured, `same_config: false` |")
@@ -142,6 +154,7 @@ w("|---|---|---|---|")
 w("| K1 `sdfk_k_sample` 1024^3 README | 2.62 ms = 6.56 TB/s | %.2f ms = %.2f TB/s | work items = 32-slice column segments handed out in memory order (DESIGN.md section 4, `tools/micro/store_*.cu`) |" % (st["sample_ms"], d["roofline"]["achieved"] / 1e3))
 w("| 1-GPU step 1024^3 | 3.73 ms = 2.88e11 voxels/s | %.2f ms = %.3g voxels/s | K1, K4a, K3, K2' below |" % (d["ms_per_step"], d["value"]))
 w("| K2' classify / K3 scans / K4a compact | 0.14 / 0.09 / 0.20 ms | %.2f / %.3f / %.2f ms | items without a sign change skipped; 16-byte count loads; active-chunk list |" % (st["classify_ms"], st["scan_ms"], st["compact_ms"]))
+w("| K4b emit (triangles + vertices) | 0.55 ms (0.15 + 0.39) | %.2f ms (%.2f + %.2f under ncu) | vertex tasks carry the cell id: the gathers no longer wait for the record (DRAM reads 0.84 -> 0.58 GB) |" % (st["emit_ms"], ncu_ms("k4b_emit_tris"), ncu_ms("k4b_emit_verts")))
 w("| fused `Sdf.ToMesh` step (device) | 1.77 ms | %.2f ms | K1d in 128-slice segments in order + the meshing changes |" % d["fused_to_mesh"]["ms_per_step"])
 w("| e2e `Sdf.ToMesh` 1024^3 | 5.46 ms (box A) | %.2f ms (this box; interleaved A/B on one box: 5.38 -> 5.17 ms) | slab cuts follow the surface, sub-ranges double, meshing stream at high priority |" % d["e2e"]["ms_per_step"])
 w("| CSG-50: sampling / e2e `Sdf.ToMesh` | 8.74 / 9.25 ms | %.2f / %.2f ms | the same |" % (c3["sample_ms"], c3["e2e"]["ms_per_step"]))
