@@ -1598,7 +1598,9 @@ mc_emit_verts_kernel(const McEmitParams p)
     // fewer vertices in flight for L2 reuse across layers (256..512 per block: 0.48..0.55 ms); the sharing cells' corners from
     // dense 32-byte "corner blocks" that K4a wrote next to the records instead of the voxel gathers (0.39 -> 0.46 ms, K4a
     // +0.025 ms: one more dependent look-up per vertex outweighs 14 fewer scattered loads -- the kernel is bound by the
-    // LATENCY of its dependent loads at 32 resident warps, which is why the tasks now carry the cell id).  The kernel moves 0.84 GB
+    // LATENCY of its dependent loads at 32 resident warps, which is why the tasks now carry the cell id); an L1 prefetch of
+    // the thread's vertex of the next kind (one address per voxel row + the two colours, from the task alone) issued before
+    // the current kind's vertex is created (0.36 -> 0.40 ms: the extra L1 traffic costs more than the overlap gains).  The kernel moves 0.84 GB
     // from DRAM for a 0.16 GB footprint of touched sectors and runs at the ~3 TB/s this box sustains for scattered sectors.)
     const McStage st = {p.verts + (size_t)first * 3, p.rgb ? p.cols + (size_t)first * 3 : reinterpret_cast<float*>(p.recipes + first),
                         p.nrms + (size_t)first * 3};
